@@ -1,0 +1,156 @@
+"""ctypes binding of libfgt_sm100a.so (the C-ABI in include/fgt_b200.h).
+
+PyTorch is used here only to own device memory and the CUDA stream; all arithmetic on the path
+is done by the kernels in the shared library. There is no CPU fallback: if the library is missing
+or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfgt_sm100a.so")
+
+ACT_NONE, ACT_LEAKY02, ACT_RELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3, 4
+AUX_NONE, AUX_ADD, AUX_MUL = 0, 1, 2
+
+_c_ll = ctypes.c_longlong
+_c_p = ctypes.c_void_p
+
+
+class FgtASeg(ctypes.Structure):
+    _fields_ = [("hi", _c_p), ("plane", _c_ll), ("C", ctypes.c_int), ("DX", ctypes.c_int),
+                ("DY", ctypes.c_int), ("DZ", ctypes.c_int), ("sx", _c_ll), ("sy", _c_ll), ("sz", _c_ll),
+                ("c_base", ctypes.c_int), ("c_per_group", ctypes.c_int), ("c_count", ctypes.c_int)]
+
+
+class FgtGemmDesc(ctypes.Structure):
+    _fields_ = [("num_segs", ctypes.c_int), ("seg", FgtASeg * 2),
+                ("kx", ctypes.c_int), ("ky", ctypes.c_int), ("kz", ctypes.c_int),
+                ("stride", ctypes.c_int), ("dil", ctypes.c_int),
+                ("pad_x", ctypes.c_int), ("pad_y", ctypes.c_int), ("pad_z", ctypes.c_int),
+                ("w_hi", _c_p), ("w_plane", _c_ll), ("N", ctypes.c_int), ("k_pad", ctypes.c_int),
+                ("groups", ctypes.c_int),
+                ("out_w", ctypes.c_int), ("out_h", ctypes.c_int), ("out_z", ctypes.c_int),
+                ("box_w", ctypes.c_int), ("box_h", ctypes.c_int), ("bn", ctypes.c_int),
+                ("bias", _c_p), ("alpha", ctypes.c_float), ("act", ctypes.c_int),
+                ("aux", _c_p), ("aux_mode", ctypes.c_int),
+                ("out_f32", _c_p), ("out_hi", _c_p), ("out_plane", _c_ll),
+                ("os_z", _c_ll), ("os_y", _c_ll), ("os_x", _c_ll), ("os_c", _c_ll),
+                ("rowmap", _c_p), ("lin_batch", ctypes.c_int)]
+
+
+_lib = None
+
+
+def load():
+    """Loads the shared library (fails loudly if it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: run `python -m fgt_b200.build` (or __graft_entry__.build()). "
+            "fgt_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.fgt_version.restype = ctypes.c_int
+    lib.fgt_last_error.restype = ctypes.c_char_p
+    lib.fgt_gemm_tc.argtypes = [ctypes.POINTER(FgtGemmDesc), _c_p]
+    lib.fgt_gemm_tc.restype = ctypes.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().fgt_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t, elem_offset=0):
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr() + elem_offset * t.element_size())
+
+
+# ------------------------------------------------------------------------------------------
+# split-bf16 tensors: a torch.bfloat16 tensor whose leading dimension (size 2) is the plane.
+# ------------------------------------------------------------------------------------------
+def to_split(x):
+    """fp32 tensor [...] -> bf16 tensor [2, ...] with hi = bf16(x), lo = bf16(x - hi)."""
+    x = x.float()
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return torch.stack([hi, lo], 0).contiguous()
+
+
+def from_split(s):
+    return s[0].float() + s[1].float()
+
+
+def empty_split(shape, device):
+    return torch.empty((2,) + tuple(shape), dtype=torch.bfloat16, device=device)
+
+
+def plane_elems(s):
+    return s[0].numel()
+
+
+class ASeg:
+    """One channel-contiguous A operand view: split tensor + logical (C, DX, DY, DZ) geometry."""
+
+    def __init__(self, split, C, DX, DY=1, DZ=1, sx=None, sy=None, sz=None, c_base=0, c_per_group=0,
+                 c_count=None, elem_offset=0):
+        self.split = split
+        self.C, self.DX, self.DY, self.DZ = C, DX, DY, DZ
+        self.sx = C if sx is None else sx
+        self.sy = self.sx * DX if sy is None else sy
+        self.sz = self.sy * DY if sz is None else sz
+        self.c_base, self.c_per_group = c_base, c_per_group
+        self.c_count = C if c_count is None else c_count
+        self.elem_offset = elem_offset
+
+
+def gemm_tc(segs, w_split, N, *, kx=1, ky=1, kz=1, stride=1, dil=1, pad_x=0, pad_y=0, pad_z=0, groups=1,
+            out_w, out_h=1, out_z=1, box_w=128, box_h=1, bn=128, bias=None, alpha=1.0, act=ACT_NONE,
+            aux=None, aux_mode=AUX_NONE, out_f32=None, out_split=None, out_elem_offset=0,
+            os_z=0, os_y=0, os_x=None, os_c=1, rowmap=None, lin_batch=0):
+    """Generic launcher for fgt_gemm_tc. Output strides are in elements; see include/fgt_b200.h."""
+    lib = load()
+    d = FgtGemmDesc()
+    d.num_segs = len(segs)
+    for i, s in enumerate(segs):
+        a = d.seg[i]
+        a.hi = s.split.data_ptr() + 2 * s.elem_offset
+        a.plane = plane_elems(s.split)
+        a.C, a.DX, a.DY, a.DZ = s.C, s.DX, s.DY, s.DZ
+        a.sx, a.sy, a.sz = s.sx, s.sy, s.sz
+        a.c_base, a.c_per_group, a.c_count = s.c_base, s.c_per_group, s.c_count
+    d.kx, d.ky, d.kz, d.stride, d.dil = kx, ky, kz, stride, dil
+    d.pad_x, d.pad_y, d.pad_z = pad_x, pad_y, pad_z
+    d.w_hi = w_split.data_ptr()
+    d.w_plane = plane_elems(w_split)
+    d.N = N
+    d.k_pad = w_split.shape[-1]
+    d.groups = groups
+    d.out_w, d.out_h, d.out_z = out_w, out_h, out_z
+    d.box_w, d.box_h, d.bn = box_w, box_h, bn
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.alpha = alpha
+    d.act = act
+    d.aux = (aux.data_ptr() + 4 * out_elem_offset) if aux is not None else None
+    d.aux_mode = aux_mode
+    d.out_f32 = (out_f32.data_ptr() + 4 * out_elem_offset) if out_f32 is not None else None
+    if out_split is not None:
+        d.out_hi = out_split.data_ptr() + 2 * out_elem_offset
+        d.out_plane = plane_elems(out_split)
+    d.os_z, d.os_y, d.os_c = os_z, os_y, os_c
+    d.os_x = N if os_x is None else os_x
+    d.rowmap = rowmap.data_ptr() if rowmap is not None else None
+    d.lin_batch = lin_batch
+    check(lib.fgt_gemm_tc(ctypes.byref(d), stream_ptr()), "fgt_gemm_tc")

@@ -1,0 +1,153 @@
+"""Seeded synthetic weights and inputs shared by tests, bench.py and tests/golden/make_golden.py.
+
+There is no network, so FGT / LAFC checkpoints (Google-Drive downloads in the reference,
+/root/reference/README.md:57) are replaced by seeded random weights of the same architecture, and
+clips by seeded synthetic frames / masks / flows shaped like the driver's tensors
+(/root/reference/tool/video_inpainting.py:689-708).
+"""
+import math
+import zlib
+
+import torch
+
+CFG_A = dict(tw=2, sw=8, gd=4, input_resolution=(240, 432), in_channel=4, cnum=64, flow_inChannel=2,
+             flow_cnum=64, frame_hidden=512, flow_hidden=256, PASSMASK=1, numBlocks=8, kernel_size=(7, 7),
+             stride=(3, 3), padding=(3, 3), num_head=4, conv_type='vanilla', norm='None', use_bias=1, ape=1,
+             mlp_ratio=40, drop=0, init_weights=1)
+
+
+def fgt_param_shapes(cfg=CFG_A):
+    """state_dict contract of FGT.models.model.Model (keys under 'net.'), SURVEY.md Appendix B;
+    restates the constructors at /root/reference/FGT/models/model.py:28-50,196-246."""
+    d, df = cfg['frame_hidden'], cfg['flow_hidden']
+    cn, fcn = cfg['cnum'], cfg['flow_cnum']
+    kh, kw = cfg['kernel_size']
+    hid = kh * kw * cfg['mlp_ratio']
+    gd = cfg['gd']
+    s = {}
+
+    def conv(name, co, ci, k1, k2=None):
+        s[name + ".weight"] = (co, ci, k1, k1 if k2 is None else k2)
+        s[name + ".bias"] = (co,)
+
+    def lin(name, co, ci):
+        s[name + ".weight"] = (co, ci)
+        s[name + ".bias"] = (co,)
+
+    def ln(name, c):
+        s[name + ".weight"] = (c,)
+        s[name + ".bias"] = (c,)
+
+    enc = [(0, 64, cfg['in_channel']), (2, 64, 64), (4, 128, 64), (6, 256, 128), (8, 384, 256), (10, 512, 320),
+           (12, 384, 192), (14, 256, 80), (16, 128, 512)]
+    for i, co, ci in enc:
+        conv(f"frame_endoder.layers.{i}", co, ci, 3)
+    conv("flow_encoder.1.featureConv", fcn, cfg['flow_inChannel'], 5)
+    conv("flow_encoder.2.featureConv", fcn * 2, fcn, 3)
+    conv("flow_encoder.3.featureConv", fcn * 2, fcn * 2, 3)
+    conv("flow_encoder.4.featureConv", fcn * 2, fcn * 2, 3)
+    conv("patch2vec", d, cn * 2, kh, kw)
+    conv("f_patch2vec", df, fcn * 2, kh, kw)
+    conv("add_pos_emb.proj", d, 1, 3)
+
+    def ffn(pre):
+        lin(pre + "ffn.conv1", hid, d)
+        lin(pre + "ffn.conv2.2", d, hid)
+
+    def tblock(pre):
+        for nm in ("query_embedding", "key_embedding", "value_embedding", "output_linear"):
+            lin(pre + "attention." + nm, d, d)
+        ffn(pre)
+        ln(pre + "norm1", d)
+        ln(pre + "norm2", d)
+
+    def sblock(pre):
+        lin(pre + "attention.query_embedding", d, d + df)
+        lin(pre + "attention.key_embedding", d, d + df)
+        lin(pre + "attention.value_embedding", d, d)
+        lin(pre + "attention.output_linear", d, d)
+        conv(pre + "attention.global_extract_v", d, 1, gd)
+        conv(pre + "attention.global_extract_k", d + df, 1, gd)
+        ln(pre + "attention.q_norm", d + df)
+        ln(pre + "attention.k_norm", d + df)
+        ln(pre + "attention.v_norm", d)
+        lin(pre + "attention.reweightFlow.0", df, d + df)
+        ffn(pre)
+        ln(pre + "norm", d)
+
+    for i in range(cfg['numBlocks'] // 2 - 1):
+        tblock(f"transformer.{i}.t_transformer.")
+        sblock(f"transformer.{i}.s_transformer.")
+    tblock("first_t_transformer.")
+    sblock("first_s_transformer.")
+    lin("vec2patch.embedding", kh * kw * cn * 2, d)
+    conv("decoder.layer1.conv.featureConv", cn * 2, cn * 2, 3)
+    conv("decoder.layer2.featureConv", cn, cn * 2, 3)
+    conv("decoder.layer3.conv.featureConv", cn, cn, 3)
+    conv("decoder.final.featureConv", 3, cn, 3)
+    return {"net." + k: v for k, v in s.items()}
+
+
+def make_state_dict(shapes, seed=0, regime="scaled"):
+    """Deterministic weights, independent of key order (each tensor seeded by crc32(key)).
+
+    regime 'default': the reference init (normal(0, 0.02) weights, zero bias, LN = identity;
+        /root/reference/FGT/models/BaseNetwork.py:20-46).
+    regime 'scaled': variance-preserving weights (std = 1.3/sqrt(fan_in)), random biases and LN
+        affines — keeps activations O(1) through the depth and makes softmax / LN non-degenerate
+        (with the default init attention logits are ~0 and softmax bugs go unseen).
+    """
+    sd = {}
+    for key, shape in shapes.items():
+        g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(key.encode())) & 0x7FFFFFFF)
+        is_norm = ("norm" in key.split(".")[-2]) if len(key.split(".")) >= 2 else False
+        if key.endswith(".weight") and len(shape) >= 2:
+            fan_in = 1
+            for s in shape[1:]:
+                fan_in *= s
+            std = 0.02 if regime == "default" else 1.3 / math.sqrt(fan_in)
+            sd[key] = torch.randn(shape, generator=g) * std
+        elif key.endswith(".weight"):  # LayerNorm gamma
+            sd[key] = torch.ones(shape) if regime == "default" else 1.0 + 0.2 * torch.randn(shape, generator=g)
+        else:  # biases / LN beta
+            if regime == "default":
+                sd[key] = torch.zeros(shape)
+            else:
+                sd[key] = (0.1 if is_norm else 0.05) * torch.randn(shape, generator=g)
+    return sd
+
+
+def _smooth(noise, k=15):
+    pad = k // 2
+    ker = torch.ones(1, 1, k, k) / (k * k)
+    n, c, h, w = noise.shape
+    x = torch.nn.functional.pad(noise.reshape(n * c, 1, h, w), (pad, pad, pad, pad), mode="reflect")
+    return torch.nn.functional.conv2d(x, ker).reshape(n, c, h, w)
+
+
+def fgt_inputs(seed=0, t=10, H=240, W=432, b=1):
+    """Synthetic clip shaped like the driver's FGT inputs (video_inpainting.py:689-708):
+    frames in [-1,1] already multiplied by (1-mask), masks in {0,1} (seeded rectangles/ellipses
+    covering roughly 10-30%), flows normalised per (frame, channel) by the signed max
+    (video_inpainting.py:402-407)."""
+    g = torch.Generator().manual_seed(seed)
+    frames = torch.rand(b, t, 3, H, W, generator=g) * 2 - 1
+    masks = torch.zeros(b, t, 1, H, W)
+    ys = torch.arange(H).view(H, 1).float()
+    xs = torch.arange(W).view(1, W).float()
+    for bi in range(b):
+        for ti in range(t):
+            r = torch.rand(5, generator=g)
+            hh = int(H * (0.3 + 0.25 * r[0].item()))
+            ww = int(W * (0.3 + 0.25 * r[1].item()))
+            y0 = int((H - hh) * r[2].item())
+            x0 = int((W - ww) * r[3].item())
+            if r[4].item() < 0.5:
+                masks[bi, ti, 0, y0:y0 + hh, x0:x0 + ww] = 1.0
+            else:
+                cy, cx = y0 + hh / 2, x0 + ww / 2
+                masks[bi, ti, 0] = ((((ys - cy) / (hh / 2)) ** 2 + ((xs - cx) / (ww / 2)) ** 2) <= 1.0).float()
+    flows = _smooth(torch.randn(b * t, 2, H, W, generator=g)) * 3.0 * 15
+    mx = flows.amax(dim=(2, 3), keepdim=True)
+    flows = (flows / mx).reshape(b, t, 2, H, W)
+    return frames * (1 - masks), flows, masks

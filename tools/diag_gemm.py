@@ -1,0 +1,125 @@
+"""GPU bring-up diagnostic for the tcgen05 GEMM engine: runs cases from trivial to complex and
+prints error statistics (and error structure for the first failure). Run under gpurun."""
+import sys
+import os
+import traceback
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from fgt_b200 import lib, packing  # noqa: E402
+
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+
+
+def report(name, got, ref, tol=2e-4):
+    got = got.double().cpu()
+    ref = ref.double().cpu()
+    err = (got - ref).abs()
+    rel = (got - ref).norm() / (ref.norm() + 1e-30)
+    mx = err.max().item() / (ref.abs().max().item() + 1e-30)
+    ok = rel < tol and mx < tol and torch.isfinite(got).all()
+    print(f"[{'OK' if ok else 'FAIL'}] {name}: rel_l2={rel:.3e} max/max={mx:.3e} shape={tuple(got.shape)}", flush=True)
+    if not ok:
+        g2 = got.reshape(-1, got.shape[-1])
+        r2 = ref.reshape(-1, ref.shape[-1])
+        e2 = (g2 - r2).abs()
+        print("  row err (first 16 rows):", [f"{v:.2e}" for v in e2.max(1).values[:16].tolist()])
+        print("  col err (first 16 cols):", [f"{v:.2e}" for v in e2.max(0).values[:16].tolist()])
+        print("  got[0,:8]", g2[0, :8].tolist())
+        print("  ref[0,:8]", r2[0, :8].tolist())
+        print("  nan count", torch.isnan(g2).sum().item(), "zeros", (g2 == 0).sum().item(), "/", g2.numel())
+    return ok
+
+
+def linear_case(M, N, K, bn=128, bias=True, act=lib.ACT_NONE, split_out=False, aux_mode=lib.AUX_NONE, scale=1.0):
+    a = torch.randn(M, K, device=dev) * scale
+    w = torch.randn(N, K, device=dev) / K ** 0.5
+    b = torch.randn(N, device=dev) if bias else None
+    a_s = lib.to_split(a)
+    w_s = packing.pack_weight(w).to(dev)
+    out = torch.full((M, N), float("nan"), device=dev)
+    out_s = lib.empty_split((M, N), dev) if split_out else None
+    aux = torch.randn(M, N, device=dev) if aux_mode else None
+    lib.gemm_tc([lib.ASeg(a_s, K, M)], w_s, N, out_w=M, bn=bn, bias=b, act=act, out_f32=out, out_split=out_s,
+                aux=aux, aux_mode=aux_mode)
+    torch.cuda.synchronize()
+    ref = a.double() @ w.double().t()
+    if bias:
+        ref = ref + b.double()
+    if act == lib.ACT_LEAKY02:
+        ref = F.leaky_relu(ref, 0.2)
+    elif act == lib.ACT_RELU:
+        ref = F.relu(ref)
+    elif act == lib.ACT_SIGMOID:
+        ref = torch.sigmoid(ref)
+    elif act == lib.ACT_TANH:
+        ref = torch.tanh(ref)
+    if aux_mode == lib.AUX_ADD:
+        ref = ref + aux.double()
+    elif aux_mode == lib.AUX_MUL:
+        ref = ref * aux.double()
+    ok = report(f"linear M={M} N={N} K={K} bn={bn} act={act} aux={aux_mode}", out, ref)
+    if split_out:
+        ok &= report("  split output", lib.from_split(out_s), ref, tol=2e-4)
+    return ok
+
+
+def conv_case(n, h, w, cin, cout, k, stride=1, pad=None, dil=1, groups=1, bn=64, box=(16, 8), act=lib.ACT_LEAKY02):
+    pad = (k // 2) * dil if pad is None else pad
+    x = torch.randn(n, cin, h, w, device=dev)
+    wt = torch.randn(cout, cin // groups, k, k, device=dev) / (cin // groups * k * k) ** 0.5
+    b = torch.randn(cout, device=dev)
+    ref = F.conv2d(x.double(), wt.double(), b.double(), stride=stride, padding=pad, dilation=dil, groups=groups)
+    if act == lib.ACT_LEAKY02:
+        ref = F.leaky_relu(ref, 0.2)
+    oh, ow = ref.shape[2], ref.shape[3]
+    x_s = lib.to_split(x.permute(0, 2, 3, 1).contiguous())  # [2, n, h, w, c]
+    w_s = packing.pack_weight(wt).to(dev)
+    out = torch.full((n, oh, ow, cout), float("nan"), device=dev)
+    seg = lib.ASeg(x_s, cin, w, h, n, c_per_group=(cin // groups if groups > 1 else 0), c_count=cin // groups)
+    lib.gemm_tc([seg], w_s, cout, kx=k, ky=k, stride=stride, dil=dil, pad_x=pad, pad_y=pad, groups=groups,
+                out_w=ow, out_h=oh, out_z=n, box_w=box[0], box_h=box[1], bn=bn, bias=b, act=act, out_f32=out,
+                os_z=oh * ow * cout, os_y=ow * cout, os_x=cout, os_c=1)
+    torch.cuda.synchronize()
+    return report(f"conv n={n} {h}x{w} cin={cin} cout={cout} k={k} s={stride} p={pad} d={dil} g={groups} bn={bn}",
+                  out.permute(0, 3, 1, 2), ref)
+
+
+def main():
+    print(torch.cuda.get_device_name(0), "lib version", lib.load().fgt_version(), flush=True)
+    cases = [
+        lambda: linear_case(128, 128, 64, bias=False),
+        lambda: linear_case(128, 128, 128, bias=False),
+        lambda: linear_case(128, 64, 512, bn=64),
+        lambda: linear_case(256, 256, 512, bn=128),
+        lambda: linear_case(1000, 520, 1960, bn=128, act=lib.ACT_RELU, split_out=True),
+        lambda: linear_case(7200, 1536, 512, bn=256, aux_mode=lib.AUX_ADD),
+        lambda: linear_case(300, 48, 200, bn=48, act=lib.ACT_SIGMOID, aux_mode=lib.AUX_MUL),
+        lambda: linear_case(40000, 512, 512, bn=128, scale=3.0),
+        lambda: conv_case(1, 16, 32, 64, 64, 3),
+        lambda: conv_case(2, 60, 108, 128, 256, 3, bn=128),
+        lambda: conv_case(2, 61, 107, 64, 128, 3, stride=2, bn=128),
+        lambda: conv_case(1, 60, 108, 128, 512, 7, stride=3, pad=3, bn=128, act=lib.ACT_NONE),
+        lambda: conv_case(1, 30, 54, 192, 192, 3, dil=4, bn=64),
+        lambda: conv_case(2, 24, 40, 128, 256, 3, groups=2, bn=128),
+        lambda: conv_case(1, 24, 40, 8, 64, 3, bn=64),
+        lambda: conv_case(1, 20, 36, 64, 3, 3, bn=16, act=lib.ACT_NONE),
+    ]
+    nfail = 0
+    for c in cases:
+        try:
+            if not c():
+                nfail += 1
+        except Exception:
+            traceback.print_exc()
+            nfail += 1
+            break
+    print("FAILURES:", nfail, flush=True)
+    return 1 if nfail else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
