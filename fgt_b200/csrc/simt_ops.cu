@@ -1,0 +1,376 @@
+// HBM-bound helper kernels around the tensor-core engine (coalesced, vectorised, warp-shuffle
+// reductions): layout packing, LayerNorm statistics, depthwise pooling / positional conv,
+// fold / unfold of the fusion FFN, nearest upsampling. No tensor cores here on purpose.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace fgt {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void store_split4(__nv_bfloat16* hi, __nv_bfloat16* lo, float a, float b, float c,
+                                             float d) {
+  __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
+  split_bf16(a, h0, l0);
+  split_bf16(b, h1, l1);
+  split_bf16(c, h2, l2);
+  split_bf16(d, h3, l3);
+  *reinterpret_cast<uint2*>(hi) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+  *reinterpret_cast<uint2*>(lo) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+}
+
+// ------------------------------------------------------------------------------------------
+// pack: NCHW fp32 (two sources concatenated on C) -> NHWC split-bf16 with channel padding and
+// optional replication padding (ReplicationPad2d of the flow encoder, model.py:207).
+// ------------------------------------------------------------------------------------------
+__global__ void pack_nchw_kernel(const float* __restrict__ s0, int c0, const float* __restrict__ s1, int c1, int n,
+                                 int H, int W, int pad, int cpad, __nv_bfloat16* __restrict__ hi, long long plane) {
+  const int Wp = W + 2 * pad, Hp = H + 2 * pad;
+  const long long total = static_cast<long long>(n) * Hp * Wp;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % Wp);
+    const int y = static_cast<int>((i / Wp) % Hp);
+    const int b = static_cast<int>(i / (static_cast<long long>(Wp) * Hp));
+    const int sx = min(max(x - pad, 0), W - 1), sy = min(max(y - pad, 0), H - 1);
+    for (int c = 0; c < cpad; ++c) {
+      float v = 0.f;
+      if (c < c0) v = s0[((static_cast<long long>(b) * c0 + c) * H + sy) * W + sx];
+      else if (c < c0 + c1) v = s1[((static_cast<long long>(b) * c1 + (c - c0)) * H + sy) * W + sx];
+      __nv_bfloat16 h, l;
+      split_bf16(v, h, l);
+      hi[i * cpad + c] = h;
+      hi[plane + i * cpad + c] = l;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// rownorm: per-row LayerNorm statistics (no affine: gamma/beta are folded into the consuming
+// Linear) over the concatenation of up to two fp32 sources; optional gather map (dest row ->
+// source row, <0 = write zeros: the reference's zero padding happens before/after LN in a way that
+// makes padded rows exactly the LN bias, attention_flow.py:122-143, attention_base.py:87-92).
+// One warp per destination row; two-pass mean / variance in registers.
+// ------------------------------------------------------------------------------------------
+constexpr int kNormMaxVec = 8;  // up to 8 float4 per lane -> C <= 1024
+
+__global__ void rownorm_kernel(const float* __restrict__ a, int ca, int lda, const float* __restrict__ b, int cb,
+                               int ldb, const int* __restrict__ gather, int rows_per_batch, long long total_rows,
+                               int dst_batch_rows, int dst_row0, __nv_bfloat16* __restrict__ hi, long long plane,
+                               float eps) {
+  const int C = ca + cb;
+  const int lane = threadIdx.x & 31;
+  const long long warp_id = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const int nvec = C / 4;
+  for (long long d = warp_id; d < total_rows; d += nwarps) {
+    const long long bidx = d / rows_per_batch;
+    const long long drow = bidx * dst_batch_rows + dst_row0 + (d - bidx * rows_per_batch);
+    __nv_bfloat16* oh = hi + drow * C;
+    __nv_bfloat16* ol = oh + plane;
+    long long src = d;
+    if (gather) src = gather[d];
+    if (src < 0) {
+      for (int v = lane; v < nvec; v += 32) {
+        *reinterpret_cast<uint2*>(oh + v * 4) = make_uint2(0u, 0u);
+        *reinterpret_cast<uint2*>(ol + v * 4) = make_uint2(0u, 0u);
+      }
+      continue;
+    }
+    float4 val[kNormMaxVec];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kNormMaxVec; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        const int c = v * 4;
+        val[i] = (c < ca) ? __ldg(reinterpret_cast<const float4*>(a + src * lda + c))
+                          : __ldg(reinterpret_cast<const float4*>(b + src * ldb + (c - ca)));
+        sum += (val[i].x + val[i].y) + (val[i].z + val[i].w);
+      }
+    }
+    const float mean = warp_sum(sum) / static_cast<float>(C);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < kNormMaxVec; ++i) {
+      if (lane + 32 * i < nvec) {
+        const float dx = val[i].x - mean, dy = val[i].y - mean, dz = val[i].z - mean, dw = val[i].w - mean;
+        sq += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(C) + eps);
+#pragma unroll
+    for (int i = 0; i < kNormMaxVec; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec)
+        store_split4(oh + v * 4, ol + v * 4, (val[i].x - mean) * rstd, (val[i].y - mean) * rstd,
+                     (val[i].z - mean) * rstd, (val[i].w - mean) * rstd);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// dwpool: depthwise k x k / stride k convolution (+bias) over the zero-padded token grid of the
+// channel concatenation [a ; b] -> fp32 pooled tokens (global_extract_k / global_extract_v,
+// attention_flow.py:44-48,135,145).
+// ------------------------------------------------------------------------------------------
+__global__ void dwpool_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb, int bt,
+                              int h, int w, int k, int gh, int gw, const float* __restrict__ wt,
+                              const float* __restrict__ bias, float* __restrict__ out) {
+  const int C = ca + cb;
+  const long long total = static_cast<long long>(bt) * gh * gw * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const long long t = i / C;
+    const int gx = static_cast<int>(t % gw);
+    const int gy = static_cast<int>((t / gw) % gh);
+    const int f = static_cast<int>(t / (static_cast<long long>(gw) * gh));
+    float acc = bias[c];
+    for (int ky = 0; ky < k; ++ky) {
+      const int y = gy * k + ky;
+      if (y >= h) break;
+      for (int kx = 0; kx < k; ++kx) {
+        const int x = gx * k + kx;
+        if (x >= w) break;
+        const long long tok = (static_cast<long long>(f) * h + y) * w + x;
+        const float v = (c < ca) ? a[tok * ca + c] : b[tok * cb + (c - ca)];
+        acc += wt[(c * k + ky) * k + kx] * v;
+      }
+    }
+    out[i] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// dwconv3x3 + identity on the token grid (AddPosEmb, model.py:75-88); writes fp32 and split.
+// ------------------------------------------------------------------------------------------
+__global__ void dwconv3_res_kernel(const float* __restrict__ x, int bt, int h, int w, int C,
+                                   const float* __restrict__ wt, const float* __restrict__ bias,
+                                   float* __restrict__ out, __nv_bfloat16* __restrict__ hi, long long plane) {
+  const long long total = static_cast<long long>(bt) * h * w * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const long long t = i / C;
+    const int px = static_cast<int>(t % w);
+    const int py = static_cast<int>((t / w) % h);
+    const long long f = t / (static_cast<long long>(w) * h);
+    float acc = bias[c];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int y = py + ky - 1;
+      if (y < 0 || y >= h) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = px + kx - 1;
+        if (xx < 0 || xx >= w) continue;
+        acc += wt[c * 9 + ky * 3 + kx] * x[((f * h + y) * w + xx) * C + c];
+      }
+    }
+    const float v = acc + x[i];
+    out[i] = v;
+    if (hi) {
+      __nv_bfloat16 hh, ll;
+      split_bf16(v, hh, ll);
+      hi[i] = hh;
+      hi[plane + i] = ll;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fold: overlap-add of per-token patches back to the feature map (nn.Fold, ffn_base.py:57-75 /
+// model.py:103-109). The hidden vector of a token is stored position-major: index p*C + c with
+// p = ky*kw + kx (the Linear's output rows are permuted accordingly at weight-pack time), so
+// both the gather here and the scatter in unfold are coalesced along c.
+//   img[b,y,x,c] = scale(y,x) * sum_{patches covering (y,x)} hid[b, token, p, c]   (+ add[b,y,x,c])
+// scale = 1/coverage-count when `normalize` (FusionFeedForward) else 1 (Vec2Patch).
+// ------------------------------------------------------------------------------------------
+__global__ void fold_kernel(const float* __restrict__ hid, int bt, int th, int tw, int C, int kh, int kw, int st,
+                            int pd, int OH, int OW, int normalize, const float* __restrict__ add,
+                            float* __restrict__ out, __nv_bfloat16* __restrict__ hi, long long plane) {
+  const int C4 = C / 4;
+  const long long total = static_cast<long long>(bt) * OH * OW * C4;
+  const int hidden = kh * kw * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C4) * 4;
+    const long long pix = i / C4;
+    const int x = static_cast<int>(pix % OW);
+    const int y = static_cast<int>((pix / OW) % OH);
+    const long long f = pix / (static_cast<long long>(OW) * OH);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cnt = 0;
+    // tokens ty with 0 <= y + pd - st*ty < kh
+    const int ty_hi = min((y + pd) / st, th - 1);
+    const int tx_hi = min((x + pd) / st, tw - 1);
+    for (int ty = ty_hi; ty >= 0; --ty) {
+      const int ky = y + pd - st * ty;
+      if (ky >= kh) break;
+      for (int tx = tx_hi; tx >= 0; --tx) {
+        const int kx = x + pd - st * tx;
+        if (kx >= kw) break;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(
+            hid + ((f * th + ty) * tw + tx) * hidden + (ky * kw + kx) * C + c));
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        ++cnt;
+      }
+    }
+    if (normalize) {
+      const float s = 1.f / static_cast<float>(cnt);
+      acc.x *= s; acc.y *= s; acc.z *= s; acc.w *= s;
+    }
+    const long long o = pix * C + c;
+    if (add) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(add + o));
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+    if (out) *reinterpret_cast<float4*>(out + o) = acc;
+    if (hi) store_split4(hi + o, hi + plane + o, acc.x, acc.y, acc.z, acc.w);
+  }
+}
+
+// unfold (+ReLU): feature map -> per-token patches, split-bf16 (nn.Unfold + ReLU, ffn_base.py:57-75,40).
+__global__ void unfold_kernel(const float* __restrict__ img, int bt, int th, int tw, int C, int kh, int kw, int st,
+                              int pd, int OH, int OW, int relu, __nv_bfloat16* __restrict__ hi, long long plane) {
+  const int C4 = C / 4;
+  const int P = kh * kw;
+  const long long total = static_cast<long long>(bt) * th * tw * P * C4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C4) * 4;
+    long long r = i / C4;
+    const int pidx = static_cast<int>(r % P);
+    r /= P;
+    const int tx = static_cast<int>(r % tw);
+    const int ty = static_cast<int>((r / tw) % th);
+    const long long f = r / (static_cast<long long>(tw) * th);
+    const int y = ty * st + pidx / kw - pd;
+    const int x = tx * st + pidx % kw - pd;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (y >= 0 && y < OH && x >= 0 && x < OW)
+      v = __ldg(reinterpret_cast<const float4*>(img + ((f * OH + y) * OW + x) * C + c));
+    if (relu) {
+      v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    }
+    const long long o = i * 4;  // == ((f*th+ty)*tw+tx)*P*C + pidx*C + c
+    store_split4(hi + o, hi + plane + o, v.x, v.y, v.z, v.w);
+  }
+}
+
+// nearest x2 upsampling of an NHWC split tensor (F.interpolate(scale_factor=2), network_blocks_2d.py:58-60)
+__global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ in, long long in_plane, int n, int H, int W,
+                                  int C, __nv_bfloat16* __restrict__ out, long long out_plane) {
+  const int C8 = C / 8;
+  const long long total = 2LL * n * (2 * H) * (2 * W) * C8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C8) * 8;
+    long long r = i / C8;
+    const int x = static_cast<int>(r % (2 * W));
+    r /= (2 * W);
+    const int y = static_cast<int>(r % (2 * H));
+    r /= (2 * H);
+    const int b = static_cast<int>(r % n);
+    const int pl = static_cast<int>(r / n);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(
+        in + pl * in_plane + ((static_cast<long long>(b) * H + (y >> 1)) * W + (x >> 1)) * C + c));
+    *reinterpret_cast<uint4*>(out + pl * out_plane + ((static_cast<long long>(b) * 2 * H + y) * 2 * W + x) * C + c) = v;
+  }
+}
+
+static int grid_for(long long work_items, int block) {
+  long long g = (work_items + block - 1) / block;
+  const long long cap = static_cast<long long>(num_sms()) * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace fgt
+
+using namespace fgt;
+
+extern "C" int fgt_pack_nchw(const float* src0, int c0, const float* src1, int c1, int n, int H, int W, int pad,
+                             int cpad, void* out_hi, long long out_plane, fgt_stream_t stream) {
+  FGT_REQUIRE(src0 && c0 >= 1 && c0 + c1 <= cpad && cpad % 8 == 0 && (c1 == 0 || src1), FGT_ERR_ARG,
+              "pack_nchw: c0=%d c1=%d cpad=%d", c0, c1, cpad);
+  const long long total = static_cast<long long>(n) * (H + 2 * pad) * (W + 2 * pad);
+  pack_nchw_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src0, c0, src1, c1, n, H, W, pad, cpad, reinterpret_cast<__nv_bfloat16*>(out_hi), out_plane);
+  FGT_CUDA(cudaGetLastError());
+  return FGT_OK;
+}
+
+extern "C" int fgt_rownorm(const float* a, int ca, int lda, const float* b, int cb, int ldb, const int* gather,
+                           int rows_per_batch, long long total_rows, int dst_batch_rows, int dst_row0,
+                           void* out_hi, long long out_plane, float eps, fgt_stream_t stream) {
+  const int C = ca + cb;
+  FGT_REQUIRE(a && ca % 4 == 0 && cb % 4 == 0 && C <= 128 * kNormMaxVec && lda % 4 == 0 && (cb == 0 || (b && ldb % 4 == 0)),
+              FGT_ERR_ARG, "rownorm: ca=%d cb=%d lda=%d ldb=%d", ca, cb, lda, ldb);
+  FGT_REQUIRE(rows_per_batch >= 1 && total_rows >= 1, FGT_ERR_ARG, "rownorm: rows");
+  const int block = 256;
+  rownorm_kernel<<<grid_for(total_rows * 32, block), block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      a, ca, lda, b, cb, ldb, gather, rows_per_batch, total_rows, dst_batch_rows, dst_row0,
+      reinterpret_cast<__nv_bfloat16*>(out_hi), out_plane, eps);
+  FGT_CUDA(cudaGetLastError());
+  return FGT_OK;
+}
+
+extern "C" int fgt_dwpool(const float* a, int ca, const float* b, int cb, int bt, int h, int w, int k, int gh,
+                          int gw, const float* weight, const float* bias, float* out, fgt_stream_t stream) {
+  FGT_REQUIRE(a && weight && bias && out && k >= 1 && gh >= 1 && gw >= 1, FGT_ERR_ARG, "dwpool: bad argument");
+  const long long total = static_cast<long long>(bt) * gh * gw * (ca + cb);
+  dwpool_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, ca, b, cb, bt, h, w, k,
+                                                                                        gh, gw, weight, bias, out);
+  FGT_CUDA(cudaGetLastError());
+  return FGT_OK;
+}
+
+extern "C" int fgt_dwconv3x3_res(const float* x, int bt, int h, int w, int C, const float* weight, const float* bias,
+                                 float* out, void* out_hi, long long out_plane, fgt_stream_t stream) {
+  FGT_REQUIRE(x && weight && bias && out, FGT_ERR_ARG, "dwconv3x3_res: null argument");
+  const long long total = static_cast<long long>(bt) * h * w * C;
+  dwconv3_res_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, bt, h, w, C, weight, bias, out, reinterpret_cast<__nv_bfloat16*>(out_hi), out_plane);
+  FGT_CUDA(cudaGetLastError());
+  return FGT_OK;
+}
+
+extern "C" int fgt_fold(const float* hid, int bt, int th, int tw, int C, int kh, int kw, int stride, int pad, int OH,
+                        int OW, int normalize, const float* add, float* out, void* out_hi, long long out_plane,
+                        fgt_stream_t stream) {
+  FGT_REQUIRE(hid && C % 4 == 0 && (out || out_hi), FGT_ERR_ARG, "fold: C=%d", C);
+  const long long total = static_cast<long long>(bt) * OH * OW * (C / 4);
+  fold_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      hid, bt, th, tw, C, kh, kw, stride, pad, OH, OW, normalize, add, out, reinterpret_cast<__nv_bfloat16*>(out_hi),
+      out_plane);
+  FGT_CUDA(cudaGetLastError());
+  return FGT_OK;
+}
+
+extern "C" int fgt_unfold(const float* img, int bt, int th, int tw, int C, int kh, int kw, int stride, int pad,
+                          int OH, int OW, int relu, void* out_hi, long long out_plane, fgt_stream_t stream) {
+  FGT_REQUIRE(img && out_hi && C % 4 == 0, FGT_ERR_ARG, "unfold: C=%d", C);
+  const long long total = static_cast<long long>(bt) * th * tw * kh * kw * (C / 4);
+  unfold_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      img, bt, th, tw, C, kh, kw, stride, pad, OH, OW, relu, reinterpret_cast<__nv_bfloat16*>(out_hi), out_plane);
+  FGT_CUDA(cudaGetLastError());
+  return FGT_OK;
+}
+
+extern "C" int fgt_upsample2x(const void* in_hi, long long in_plane, int n, int H, int W, int C, void* out_hi,
+                              long long out_plane, fgt_stream_t stream) {
+  FGT_REQUIRE(in_hi && out_hi && C % 8 == 0, FGT_ERR_ARG, "upsample2x: C=%d", C);
+  const long long total = 2LL * n * (2 * H) * (2 * W) * (C / 8);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(in_hi), in_plane, n, H, W, C, reinterpret_cast<__nv_bfloat16*>(out_hi),
+      out_plane);
+  FGT_CUDA(cudaGetLastError());
+  return FGT_OK;
+}

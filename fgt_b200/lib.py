@@ -41,6 +41,17 @@ class FgtGemmDesc(ctypes.Structure):
                 ("rowmap", _c_p), ("lin_batch", ctypes.c_int)]
 
 
+class FgtAttnDesc(ctypes.Structure):
+    _fields_ = [("q_hi", _c_p), ("q_plane", _c_ll), ("q_batch_stride", _c_ll), ("q_ld", ctypes.c_int),
+                ("k_hi", _c_p), ("k_plane", _c_ll), ("k_batch_stride", _c_ll), ("k_ld", ctypes.c_int),
+                ("vt_hi", _c_p), ("vt_plane", _c_ll), ("vt_batch_stride", _c_ll), ("vt_ld", ctypes.c_int),
+                ("out_hi", _c_p), ("out_plane", _c_ll), ("out_batch_stride", _c_ll), ("out_ld", ctypes.c_int),
+                ("batches", ctypes.c_int), ("heads", ctypes.c_int), ("head_dim", ctypes.c_int),
+                ("Lq", ctypes.c_int), ("Lk", ctypes.c_int), ("Lk_rows", ctypes.c_int),
+                ("scale", ctypes.c_float), ("mode", ctypes.c_int),
+                ("glob_start", ctypes.c_int), ("glob_count", ctypes.c_int)]
+
+
 _lib = None
 
 
@@ -58,6 +69,19 @@ def load():
     lib.fgt_last_error.restype = ctypes.c_char_p
     lib.fgt_gemm_tc.argtypes = [ctypes.POINTER(FgtGemmDesc), _c_p]
     lib.fgt_gemm_tc.restype = ctypes.c_int
+    lib.fgt_attention.argtypes = [ctypes.POINTER(FgtAttnDesc), _c_p]
+    lib.fgt_attention.restype = ctypes.c_int
+    ci, cf, cll = ctypes.c_int, ctypes.c_float, _c_ll
+    lib.fgt_pack_nchw.argtypes = [_c_p, ci, _c_p, ci, ci, ci, ci, ci, ci, _c_p, cll, _c_p]
+    lib.fgt_rownorm.argtypes = [_c_p, ci, ci, _c_p, ci, ci, _c_p, ci, cll, ci, ci, _c_p, cll, cf, _c_p]
+    lib.fgt_dwpool.argtypes = [_c_p, ci, _c_p, ci, ci, ci, ci, ci, ci, ci, _c_p, _c_p, _c_p, _c_p]
+    lib.fgt_dwconv3x3_res.argtypes = [_c_p, ci, ci, ci, ci, _c_p, _c_p, _c_p, _c_p, cll, _c_p]
+    lib.fgt_fold.argtypes = [_c_p, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, _c_p, _c_p, _c_p, cll, _c_p]
+    lib.fgt_unfold.argtypes = [_c_p, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, _c_p, cll, _c_p]
+    lib.fgt_upsample2x.argtypes = [_c_p, cll, ci, ci, ci, ci, _c_p, cll, _c_p]
+    for fn in (lib.fgt_pack_nchw, lib.fgt_rownorm, lib.fgt_dwpool, lib.fgt_dwconv3x3_res, lib.fgt_fold,
+               lib.fgt_unfold, lib.fgt_upsample2x):
+        fn.restype = ctypes.c_int
     _lib = lib
     return lib
 
@@ -154,3 +178,71 @@ def gemm_tc(segs, w_split, N, *, kx=1, ky=1, kz=1, stride=1, dil=1, pad_x=0, pad
     d.rowmap = rowmap.data_ptr() if rowmap is not None else None
     d.lin_batch = lin_batch
     check(lib.fgt_gemm_tc(ctypes.byref(d), stream_ptr()), "fgt_gemm_tc")
+
+
+def attention(q, k, vt, out, *, batches, heads, Lq, Lk, Lk_rows=None, q_ld, k_ld, vt_ld, out_ld,
+              q_batch_stride, k_batch_stride, vt_batch_stride, out_batch_stride, scale, mode=0,
+              glob_start=0, glob_count=0, q_off=0, k_off=0):
+    """fgt_attention launcher. q/k/vt/out are split-bf16 tensors; strides in elements; q_off/k_off are
+    element offsets into the plane (e.g. when Q and K share one [rows, 2*C] buffer)."""
+    lib = load()
+    d = FgtAttnDesc()
+    d.q_hi, d.q_plane, d.q_batch_stride, d.q_ld = q.data_ptr() + 2 * q_off, plane_elems(q), q_batch_stride, q_ld
+    d.k_hi, d.k_plane, d.k_batch_stride, d.k_ld = k.data_ptr() + 2 * k_off, plane_elems(k), k_batch_stride, k_ld
+    d.vt_hi, d.vt_plane, d.vt_batch_stride, d.vt_ld = vt.data_ptr(), plane_elems(vt), vt_batch_stride, vt_ld
+    d.out_hi, d.out_plane, d.out_batch_stride, d.out_ld = out.data_ptr(), plane_elems(out), out_batch_stride, out_ld
+    d.batches, d.heads, d.head_dim = batches, heads, 128
+    d.Lq, d.Lk = Lq, Lk
+    d.Lk_rows = Lk if Lk_rows is None else Lk_rows
+    d.scale, d.mode, d.glob_start, d.glob_count = scale, mode, glob_start, glob_count
+    check(lib.fgt_attention(ctypes.byref(d), stream_ptr()), "fgt_attention")
+
+
+def _dp(t):
+    return t.data_ptr() if t is not None else None
+
+
+def pack_nchw(src0, src1, out_split, pad=0):
+    """[n,c0,H,W] (+ [n,c1,H,W]) fp32 -> NHWC split [2, n, H+2p, W+2p, cpad] with replication pad."""
+    n, c0, H, W = src0.shape
+    c1 = src1.shape[1] if src1 is not None else 0
+    cpad = out_split.shape[-1]
+    check(load().fgt_pack_nchw(_dp(src0), c0, _dp(src1), c1, n, H, W, pad, cpad, _dp(out_split),
+                               plane_elems(out_split), stream_ptr()), "fgt_pack_nchw")
+
+
+def rownorm(a, b, out_split, *, gather=None, rows_per_batch, total_rows, dst_batch_rows, dst_row0=0, eps=1e-5):
+    ca, lda = a.shape[-1], a.shape[-1]
+    cb, ldb = (b.shape[-1], b.shape[-1]) if b is not None else (0, 0)
+    check(load().fgt_rownorm(_dp(a), ca, lda, _dp(b), cb, ldb, _dp(gather), rows_per_batch, total_rows,
+                             dst_batch_rows, dst_row0, _dp(out_split), plane_elems(out_split), eps, stream_ptr()),
+          "fgt_rownorm")
+
+
+def dwpool(a, b, bt, h, w, k, gh, gw, weight, bias, out):
+    ca = a.shape[-1]
+    cb = b.shape[-1] if b is not None else 0
+    check(load().fgt_dwpool(_dp(a), ca, _dp(b), cb, bt, h, w, k, gh, gw, _dp(weight), _dp(bias), _dp(out),
+                            stream_ptr()), "fgt_dwpool")
+
+
+def dwconv3x3_res(x, bt, h, w, C, weight, bias, out, out_split=None):
+    check(load().fgt_dwconv3x3_res(_dp(x), bt, h, w, C, _dp(weight), _dp(bias), _dp(out), _dp(out_split),
+                                   plane_elems(out_split) if out_split is not None else 0, stream_ptr()),
+          "fgt_dwconv3x3_res")
+
+
+def fold(hid, bt, th, tw, C, kh, kw, stride, pad, OH, OW, *, normalize, add=None, out=None, out_split=None):
+    check(load().fgt_fold(_dp(hid), bt, th, tw, C, kh, kw, stride, pad, OH, OW, 1 if normalize else 0, _dp(add),
+                          _dp(out), _dp(out_split), plane_elems(out_split) if out_split is not None else 0,
+                          stream_ptr()), "fgt_fold")
+
+
+def unfold(img, bt, th, tw, C, kh, kw, stride, pad, OH, OW, out_split, relu=True):
+    check(load().fgt_unfold(_dp(img), bt, th, tw, C, kh, kw, stride, pad, OH, OW, 1 if relu else 0,
+                            _dp(out_split), plane_elems(out_split), stream_ptr()), "fgt_unfold")
+
+
+def upsample2x(in_split, n, H, W, C, out_split):
+    check(load().fgt_upsample2x(_dp(in_split), plane_elems(in_split), n, H, W, C, _dp(out_split),
+                                plane_elems(out_split), stream_ptr()), "fgt_upsample2x")

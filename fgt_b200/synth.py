@@ -93,7 +93,7 @@ def make_state_dict(shapes, seed=0, regime="scaled"):
 
     regime 'default': the reference init (normal(0, 0.02) weights, zero bias, LN = identity;
         /root/reference/FGT/models/BaseNetwork.py:20-46).
-    regime 'scaled': variance-preserving weights (std = 1.3/sqrt(fan_in)), random biases and LN
+    regime 'scaled': variance-preserving weights (std = gain/sqrt(fan_in), gain 2 on Q/K projections), random biases and LN
         affines — keeps activations O(1) through the depth and makes softmax / LN non-degenerate
         (with the default init attention logits are ~0 and softmax bugs go unseen).
     """
@@ -105,7 +105,14 @@ def make_state_dict(shapes, seed=0, regime="scaled"):
             fan_in = 1
             for s in shape[1:]:
                 fan_in *= s
-            std = 0.02 if regime == "default" else 1.3 / math.sqrt(fan_in)
+            gain = 1.0
+            if "query_embedding" in key or "key_embedding" in key:
+                gain = 2.0  # attention logits std ~3: softmax clearly non-uniform
+            elif "decoder.final" in key:
+                gain = 0.5  # keep tanh out of saturation
+            elif "vec2patch" in key:
+                gain = 0.25
+            std = 0.02 if regime == "default" else gain / math.sqrt(fan_in)
             sd[key] = torch.randn(shape, generator=g) * std
         elif key.endswith(".weight"):  # LayerNorm gamma
             sd[key] = torch.ones(shape) if regime == "default" else 1.0 + 0.2 * torch.randn(shape, generator=g)

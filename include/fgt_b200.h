@@ -102,6 +102,76 @@ typedef struct {
 
 int fgt_gemm_tc(const FgtGemmDesc* desc, fgt_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * fgt_attention: fused softmax(Q K^T * scale) V (flash-style, scores never leave the SM).
+ * Q, K: split-bf16 row-major [batch, rows, heads*128]; V is supplied TRANSPOSED,
+ * V^T: split-bf16 [batch, heads*128, vt_ld] (keys contiguous) — the V projection GEMM writes it
+ * that way directly (os_c = vt_ld, os_x = 1). Output: split-bf16 [batch, Lq, heads*128].
+ *   mode 0 (dense)   : every query row attends to keys [0, Lk)            (TMHSA zones)
+ *   mode 1 (windowed): query tile i (=two 64-token windows) attends to its own two 64-key tiles
+ *                      (block-diagonal) plus the shared keys [glob_start, glob_start+glob_count)
+ *                      (SWMHSA local window + pooled global tokens)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  const void* q_hi; long long q_plane; long long q_batch_stride; int q_ld;
+  const void* k_hi; long long k_plane; long long k_batch_stride; int k_ld;
+  const void* vt_hi; long long vt_plane; long long vt_batch_stride; int vt_ld;
+  void* out_hi; long long out_plane; long long out_batch_stride; int out_ld;
+  int batches, heads, head_dim; /* head_dim must be 128 */
+  int Lq;                       /* query rows per batch */
+  int Lk;                       /* dense: valid keys per batch */
+  int Lk_rows;                  /* addressable key rows per batch (>= Lk; windowed: local + global rows) */
+  float scale;                  /* 1/sqrt(head_dim) */
+  int mode;
+  int glob_start, glob_count;   /* windowed mode */
+} FgtAttnDesc;
+
+int fgt_attention(const FgtAttnDesc* desc, fgt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * HBM-bound helpers (coalesced / vectorised CUDA-core kernels). "split" outputs are split-bf16.
+ * ------------------------------------------------------------------------------------------ */
+
+/* NCHW fp32 (src0 channels then src1 channels) -> NHWC split with `cpad` channels (zeros beyond
+ * c0+c1) and `pad` pixels of REPLICATION padding on each side. Replaces torch.cat + view at
+ * FGT/models/model.py:253-258 and nn.ReplicationPad2d at model.py:207. */
+int fgt_pack_nchw(const float* src0, int c0, const float* src1, int c1, int n, int H, int W, int pad, int cpad,
+                  void* out_hi, long long out_plane, fgt_stream_t stream);
+
+/* LayerNorm statistics without affine (gamma/beta are folded into the consuming Linear) over the
+ * channel concatenation [a ; b] of fp32 rows. Destination row of work item d is
+ * (d / rows_per_batch) * dst_batch_rows + dst_row0 + d % rows_per_batch; its source row is
+ * gather[d] (or d when gather == NULL); gather[d] < 0 writes a zero row (the reference's F.pad).
+ * Replaces nn.LayerNorm at model.py:126,128,147 and attention_flow.py:142-143,154 together with the
+ * window / zone partition copies at attention_flow.py:132-133,150-153, attention_base.py:93-98. */
+int fgt_rownorm(const float* a, int ca, int lda, const float* b, int cb, int ldb, const int* gather,
+                int rows_per_batch, long long total_rows, int dst_batch_rows, int dst_row0, void* out_hi,
+                long long out_plane, float eps, fgt_stream_t stream);
+
+/* Depthwise k x k, stride k convolution (+bias) of the token grid [bt,h,w,ca+cb], zero-padded to
+ * (gh*k, gw*k) -> fp32 [bt, gh*gw, ca+cb]. weight is the torch layout [C,1,k,k].
+ * Replaces global_extract_k / global_extract_v, attention_flow.py:135,145. */
+int fgt_dwpool(const float* a, int ca, const float* b, int cb, int bt, int h, int w, int k, int gh, int gw,
+               const float* weight, const float* bias, float* out, fgt_stream_t stream);
+
+/* out = x + depthwise3x3(x) + bias on the token grid (AddPosEmb.forward, model.py:75-88). */
+int fgt_dwconv3x3_res(const float* x, int bt, int h, int w, int C, const float* weight, const float* bias,
+                      float* out, void* out_hi, long long out_plane, fgt_stream_t stream);
+
+/* Overlap-add fold of position-major token patches hid[bt*th*tw, (kh*kw)*C] to [bt,OH,OW,C]
+ * (optionally divided by the coverage count, optionally + add). nn.Fold at ffn_base.py:57-75 and
+ * model.py:103-109 (+ the skip add at model.py:279). */
+int fgt_fold(const float* hid, int bt, int th, int tw, int C, int kh, int kw, int stride, int pad, int OH, int OW,
+             int normalize, const float* add, float* out, void* out_hi, long long out_plane, fgt_stream_t stream);
+
+/* nn.Unfold (+ optional ReLU) of [bt,OH,OW,C] into position-major token patches (split). */
+int fgt_unfold(const float* img, int bt, int th, int tw, int C, int kh, int kw, int stride, int pad, int OH,
+               int OW, int relu, void* out_hi, long long out_plane, fgt_stream_t stream);
+
+/* Nearest x2 upsampling of an NHWC split tensor (F.interpolate at network_blocks_2d.py:58-60). */
+int fgt_upsample2x(const void* in_hi, long long in_plane, int n, int H, int W, int C, void* out_hi,
+                   long long out_plane, fgt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
