@@ -60,7 +60,8 @@ constexpr int kNormMaxVec = 8;  // up to 8 float4 per lane -> C <= 1024
 
 __global__ void rownorm_kernel(const float* __restrict__ a, int ca, int lda, const float* __restrict__ b, int cb,
                                int ldb, const int* __restrict__ gather, int rows_per_batch, long long total_rows,
-                               int dst_batch_rows, int dst_row0, __nv_bfloat16* __restrict__ hi, long long plane,
+                               int dst_batch_rows, int dst_row0, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, __nv_bfloat16* __restrict__ hi, long long plane,
                                float eps) {
   const int C = ca + cb;
   const int lane = threadIdx.x & 31;
@@ -106,9 +107,16 @@ __global__ void rownorm_kernel(const float* __restrict__ a, int ca, int lda, con
 #pragma unroll
     for (int i = 0; i < kNormMaxVec; ++i) {
       const int v = lane + 32 * i;
-      if (v < nvec)
-        store_split4(oh + v * 4, ol + v * 4, (val[i].x - mean) * rstd, (val[i].y - mean) * rstd,
-                     (val[i].z - mean) * rstd, (val[i].w - mean) * rstd);
+      if (v < nvec) {
+        float4 o = make_float4((val[i].x - mean) * rstd, (val[i].y - mean) * rstd, (val[i].z - mean) * rstd,
+                               (val[i].w - mean) * rstd);
+        if (gamma) {
+          const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + v * 4));
+          const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + v * 4));
+          o.x = o.x * gm.x + bt.x; o.y = o.y * gm.y + bt.y; o.z = o.z * gm.z + bt.z; o.w = o.w * gm.w + bt.w;
+        }
+        store_split4(oh + v * 4, ol + v * 4, o.x, o.y, o.z, o.w);
+      }
     }
   }
 }
@@ -309,14 +317,16 @@ extern "C" int fgt_pack_nchw(const float* src0, int c0, const float* src1, int c
 
 extern "C" int fgt_rownorm(const float* a, int ca, int lda, const float* b, int cb, int ldb, const int* gather,
                            int rows_per_batch, long long total_rows, int dst_batch_rows, int dst_row0,
-                           void* out_hi, long long out_plane, float eps, fgt_stream_t stream) {
+                           const float* gamma, const float* beta, void* out_hi, long long out_plane, float eps,
+                           fgt_stream_t stream) {
   const int C = ca + cb;
   FGT_REQUIRE(a && ca % 4 == 0 && cb % 4 == 0 && C <= 128 * kNormMaxVec && lda % 4 == 0 && (cb == 0 || (b && ldb % 4 == 0)),
               FGT_ERR_ARG, "rownorm: ca=%d cb=%d lda=%d ldb=%d", ca, cb, lda, ldb);
   FGT_REQUIRE(rows_per_batch >= 1 && total_rows >= 1, FGT_ERR_ARG, "rownorm: rows");
+  FGT_REQUIRE((gamma == nullptr) == (beta == nullptr), FGT_ERR_ARG, "rownorm: gamma and beta go together");
   const int block = 256;
   rownorm_kernel<<<grid_for(total_rows * 32, block), block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      a, ca, lda, b, cb, ldb, gather, rows_per_batch, total_rows, dst_batch_rows, dst_row0,
+      a, ca, lda, b, cb, ldb, gather, rows_per_batch, total_rows, dst_batch_rows, dst_row0, gamma, beta,
       reinterpret_cast<__nv_bfloat16*>(out_hi), out_plane, eps);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;

@@ -73,7 +73,7 @@ def load():
     lib.fgt_attention.restype = ctypes.c_int
     ci, cf, cll = ctypes.c_int, ctypes.c_float, _c_ll
     lib.fgt_pack_nchw.argtypes = [_c_p, ci, _c_p, ci, ci, ci, ci, ci, ci, _c_p, cll, _c_p]
-    lib.fgt_rownorm.argtypes = [_c_p, ci, ci, _c_p, ci, ci, _c_p, ci, cll, ci, ci, _c_p, cll, cf, _c_p]
+    lib.fgt_rownorm.argtypes = [_c_p, ci, ci, _c_p, ci, ci, _c_p, ci, cll, ci, ci, _c_p, _c_p, _c_p, cll, cf, _c_p]
     lib.fgt_dwpool.argtypes = [_c_p, ci, _c_p, ci, ci, ci, ci, ci, ci, ci, _c_p, _c_p, _c_p, _c_p]
     lib.fgt_dwconv3x3_res.argtypes = [_c_p, ci, ci, ci, ci, _c_p, _c_p, _c_p, _c_p, cll, _c_p]
     lib.fgt_fold.argtypes = [_c_p, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, _c_p, _c_p, _c_p, cll, _c_p]
@@ -211,11 +211,13 @@ def pack_nchw(src0, src1, out_split, pad=0):
                                plane_elems(out_split), stream_ptr()), "fgt_pack_nchw")
 
 
-def rownorm(a, b, out_split, *, gather=None, rows_per_batch, total_rows, dst_batch_rows, dst_row0=0, eps=1e-5):
+def rownorm(a, b, out_split, *, gather=None, rows_per_batch, total_rows, dst_batch_rows, dst_row0=0, eps=1e-5,
+            gamma=None, beta=None):
     ca, lda = a.shape[-1], a.shape[-1]
     cb, ldb = (b.shape[-1], b.shape[-1]) if b is not None else (0, 0)
     check(load().fgt_rownorm(_dp(a), ca, lda, _dp(b), cb, ldb, _dp(gather), rows_per_batch, total_rows,
-                             dst_batch_rows, dst_row0, _dp(out_split), plane_elems(out_split), eps, stream_ptr()),
+                             dst_batch_rows, dst_row0, _dp(gamma), _dp(beta), _dp(out_split), plane_elems(out_split),
+                             eps, stream_ptr()),
           "fgt_rownorm")
 
 

@@ -138,15 +138,15 @@ int fgt_attention(const FgtAttnDesc* desc, fgt_stream_t stream);
 int fgt_pack_nchw(const float* src0, int c0, const float* src1, int c1, int n, int H, int W, int pad, int cpad,
                   void* out_hi, long long out_plane, fgt_stream_t stream);
 
-/* LayerNorm statistics without affine (gamma/beta are folded into the consuming Linear) over the
- * channel concatenation [a ; b] of fp32 rows. Destination row of work item d is
+/* LayerNorm over the channel concatenation [a ; b] of fp32 rows. gamma/beta may be NULL (statistics
+ * only: the affine is then folded into the consuming Linear at weight-pack time). Destination row of work item d is
  * (d / rows_per_batch) * dst_batch_rows + dst_row0 + d % rows_per_batch; its source row is
  * gather[d] (or d when gather == NULL); gather[d] < 0 writes a zero row (the reference's F.pad).
  * Replaces nn.LayerNorm at model.py:126,128,147 and attention_flow.py:142-143,154 together with the
  * window / zone partition copies at attention_flow.py:132-133,150-153, attention_base.py:93-98. */
 int fgt_rownorm(const float* a, int ca, int lda, const float* b, int cb, int ldb, const int* gather,
-                int rows_per_batch, long long total_rows, int dst_batch_rows, int dst_row0, void* out_hi,
-                long long out_plane, float eps, fgt_stream_t stream);
+                int rows_per_batch, long long total_rows, int dst_batch_rows, int dst_row0, const float* gamma,
+                const float* beta, void* out_hi, long long out_plane, float eps, fgt_stream_t stream);
 
 /* Depthwise k x k, stride k convolution (+bias) of the token grid [bt,h,w,ca+cb], zero-padded to
  * (gh*k, gw*k) -> fp32 [bt, gh*gw, ca+cb]. weight is the torch layout [C,1,k,k].

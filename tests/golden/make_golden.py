@@ -1,0 +1,100 @@
+"""Generates the golden fixtures in this directory by running the UNMODIFIED reference modules
+imported from /root/reference (only available in the build container, never on the GPU box).
+
+    python tests/golden/make_golden.py
+
+Weights and inputs come from fgt_b200.synth (seeded, order-independent), so tests can regenerate
+the identical inputs anywhere and only the reference OUTPUTS are stored here. The reference has no
+tests or golden vectors of its own; these files are the pin for oracle/ and, through
+it, for the CUDA path.
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+# import order mirrors tool/video_inpainting.py:4-6 (FGT/ and LAFC/ both own a `models` package)
+sys.path[:0] = [REF, os.path.join(REF, "FGT"), os.path.join(REF, "LAFC")]
+sys.path.insert(0, ROOT)
+
+from fgt_b200 import synth  # noqa: E402
+
+VERSIONS = dict(torch=torch.__version__, numpy=np.__version__)
+
+
+def fgt_case(name, H, W, t, regime, res, seed, sample=None):
+    M = importlib.import_module("FGT.models.model")
+    cfg = dict(synth.CFG_A)
+    cfg["input_resolution"] = res
+    sd = synth.make_state_dict(synth.fgt_param_shapes(cfg), seed=seed, regime=regime)
+    torch.manual_seed(0)
+    model = M.Model(cfg)
+    model.load_state_dict(sd)
+    fr, fl, mk = synth.fgt_inputs(seed=seed + 2, t=t, H=H, W=W)
+    with torch.no_grad():
+        out = model(fr, fl, mk)
+    meta = dict(H=H, W=W, t=t, regime=regime, res=list(res), seed=seed, **VERSIONS)
+    arrs = dict(meta=np.array(repr(meta)), l2=np.float64(out.double().norm().item()),
+                mean=np.float64(out.double().mean().item()), std=np.float64(out.double().std().item()))
+    if sample is None:
+        arrs["out"] = out.numpy().astype(np.float32)
+    else:
+        g = torch.Generator().manual_seed(1234)
+        idx = torch.randperm(out.numel(), generator=g)[:sample]
+        arrs["idx"] = idx.numpy().astype(np.int64)
+        arrs["val"] = out.reshape(-1)[idx].numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrs)
+    print(name, "out std", out.std().item(), "saved")
+
+
+def module_cases():
+    """Module-level goldens at BASELINE config 1 (single 432x240 frame, spatial MHSA) and friends."""
+    AF = importlib.import_module("FGT.models.transformer_base.attention_flow")
+    AB = importlib.import_module("FGT.models.transformer_base.attention_base")
+    FF = importlib.import_module("FGT.models.transformer_base.ffn_base")
+    shapes = synth.fgt_param_shapes(synth.CFG_A)
+    sd = synth.make_state_dict(shapes, seed=7, regime="scaled")
+    out = {}
+    g = torch.Generator().manual_seed(99)
+    x = torch.randn(2, 720, 512, generator=g)
+    f = torch.randn(2, 720, 256, generator=g)
+    # SWMHSA, constructor geometry 20x36 (config 1) ------------------------------------------
+    pre = "net.first_s_transformer.attention."
+    m = AF.SWMHSA_depthGlobalWindowConcatLN_qkFlow_reweightFlow([20, 36], 8, 4, 512, 256, 4, p=0)
+    m.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)})
+    with torch.no_grad():
+        out["swmhsa"] = m(x, f, 2).numpy()
+    # TMHSA --------------------------------------------------------------------------------------
+    pre = "net.first_t_transformer.attention."
+    m = AB.TMHSA([20, 36], 2, 512, 4, p=0)
+    m.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)})
+    with torch.no_grad():
+        out["tmhsa"] = m(x, 2).numpy()
+    # FusionFeedForward --------------------------------------------------------------------------
+    pre = "net.first_t_transformer.ffn."
+    t2t = {'kernel_size': (7, 7), 'stride': (3, 3), 'padding': (3, 3), 'output_size': (60, 108)}
+    m = FF.FusionFeedForward(512, 40, 720, t2t, p=0)
+    m.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)})
+    with torch.no_grad():
+        out["ffn"] = m(x).numpy()
+    g2 = torch.Generator().manual_seed(1234)
+    idx = torch.randperm(2 * 720 * 512, generator=g2)[:16384]
+    arrs = {"idx": idx.numpy().astype(np.int64), "meta": np.array(repr(dict(seed=7, **VERSIONS)))}
+    for k, v in out.items():
+        arrs[k] = v.reshape(-1)[idx.numpy()].astype(np.float32)
+        arrs[k + "_l2"] = np.float64(np.linalg.norm(v.astype(np.float64)))
+    np.savez_compressed(os.path.join(HERE, "fgt_modules.npz"), **arrs)
+    print("fgt_modules saved")
+
+
+if __name__ == "__main__":
+    fgt_case("fgt_small_scaled", 64, 96, 3, "scaled", (64, 96), seed=1)
+    fgt_case("fgt_small_default", 64, 96, 3, "default", (64, 96), seed=1)
+    fgt_case("fgt_runtime_geo", 72, 100, 2, "scaled", (64, 96), seed=2)
+    fgt_case("fgt_full_t10", 240, 432, 10, "scaled", (240, 432), seed=1, sample=16384)
+    module_cases()

@@ -1,0 +1,130 @@
+"""CPU: host-side logic (weight packing, LayerNorm folding, window/zone index maps, state_dict
+contract) and the C-ABI surface (library loads, exports every symbol the header declares)."""
+import ctypes
+import math
+import os
+import re
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from fgt_b200 import lib, packing, synth
+from fgt_b200.fgt_model import Model
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _small_model():
+    cfg = dict(synth.CFG_A)
+    cfg["input_resolution"] = (64, 96)
+    return Model(cfg), cfg
+
+
+def test_library_exports_header_symbols():
+    from fgt_b200 import build
+    build.build()
+    cdll = ctypes.CDLL(lib.LIB_PATH)
+    with open(os.path.join(ROOT, "include", "fgt_b200.h")) as fh:
+        header = fh.read()
+    names = set(re.findall(r"\b(fgt_[a-z0-9_]+)\s*\(", header))
+    assert {"fgt_gemm_tc", "fgt_attention", "fgt_rownorm", "fgt_fold", "fgt_unfold"} <= names
+    for n in sorted(names):
+        assert hasattr(cdll, n), f"{n} declared in include/fgt_b200.h but not exported"
+    assert lib.load().fgt_version() >= 100
+
+
+def test_no_cpu_fallback():
+    model, _ = _small_model()
+    fr, fl, mk = synth.fgt_inputs(seed=0, t=2, H=64, W=96)
+    with pytest.raises(RuntimeError):
+        model(fr, fl, mk)
+
+
+def test_state_dict_contract():
+    model, cfg = _small_model()
+    shapes = synth.fgt_param_shapes(cfg)
+    sd = model.state_dict()
+    assert set(sd.keys()) == set(shapes.keys())
+    for k, s in shapes.items():
+        assert tuple(sd[k].shape) == tuple(s), k
+    assert "net.frame_endoder.layers.0.weight" in sd  # the reference's spelling (model.py:205)
+    model.load_state_dict(synth.make_state_dict(shapes, seed=3))
+
+
+def test_split_roundtrip():
+    x = torch.randn(1000) * torch.logspace(-3, 3, 1000)
+    s = lib.to_split(x)
+    assert s.dtype == torch.bfloat16 and s.shape == (2, 1000)
+    assert ((lib.from_split(s) - x).abs() / x.abs()).max() < 2 ** -15
+
+
+def test_pack_weight_order():
+    w = torch.randn(6, 10, 3, 3)
+    p = lib.from_split(packing.pack_weight(w, [4, 6]))  # two segments -> each padded to 64
+    assert p.shape == (6, 9 * 128)
+    p = p.reshape(6, 9, 128)
+    wt = w.reshape(6, 10, 9).permute(0, 2, 1)
+    assert torch.allclose(p[:, :, 0:4], wt[:, :, 0:4], rtol=1e-4, atol=1e-6)
+    assert torch.allclose(p[:, :, 64:70], wt[:, :, 4:10], rtol=1e-4, atol=1e-6)
+    assert p[:, :, 4:64].abs().max() == 0 and p[:, :, 70:].abs().max() == 0
+
+
+def test_fold_layernorm():
+    torch.manual_seed(0)
+    x = torch.randn(50, 32)
+    w, b = torch.randn(16, 32), torch.randn(16)
+    g, be = torch.randn(32), torch.randn(32)
+    ref = F.linear(F.layer_norm(x, (32,), g, be), w, b)
+    w2, b2 = packing.fold_layernorm(w, b, g, be)
+    got = F.linear(F.layer_norm(x, (32,)), w2, b2)
+    assert torch.allclose(got, ref, rtol=1e-4, atol=1e-4)
+    # a zero row before LayerNorm becomes the LN bias (the reference's padded tokens)
+    z = F.linear(F.layer_norm(torch.zeros(1, 32), (32,), g, be), w, b)
+    assert torch.allclose(b2[None], z, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("b,t,H,W", [(1, 3, 64, 96), (1, 2, 72, 100), (2, 2, 80, 120), (1, 2, 720, 1280)])
+def test_zone_and_window_maps(b, t, H, W):
+    """The gather/scatter maps must reproduce the reference's pad + view + permute bookkeeping
+    (attention_base.py:86-98, attention_flow.py:122-133)."""
+    model, _ = _small_model()
+    g = model.net._geometry(b, t, H, W, "cpu")
+    h, w, n = g.h, g.w, g.n
+    tok = torch.arange(b * t * n).reshape(b * t, h, w, 1).float()
+    # temporal zones, as the reference does it
+    gs = 2
+    wh, ww = math.ceil(h / gs), math.ceil(w / gs)
+    pad_r, pad_b = (ww - w % ww) % ww, (wh - h % wh) % wh
+    x = F.pad(tok + 1, (0, 0, 0, pad_r, 0, pad_b)) - 1  # padded -> -1
+    nh, nw = h + pad_b, w + pad_r
+    x = x.view(b, t, gs, nh // gs, gs, nw // gs, 1, 1).permute(0, 2, 4, 6, 1, 3, 5, 7).reshape(-1)
+    assert torch.equal(x.to(torch.int32), g.zone_map)
+    assert g.Lz == t * (nh // gs) * (nw // gs) and g.zones == b * 4
+    # spatial windows
+    ws = 8
+    pad_r, pad_b = (ws - w % ws) % ws, (ws - h % ws) % ws
+    x = F.pad(tok + 1, (0, 0, 0, pad_r, 0, pad_b)) - 1
+    gh, gw = (h + pad_b) // ws, (w + pad_r) // ws
+    x = x.reshape(b * t, gh, ws, gw, ws, 1).transpose(2, 3).reshape(b * t, gh * gw * ws * ws)
+    wm = g.win_map.reshape(b * t, g.nwp * 64)
+    assert torch.equal(x.to(torch.int32), wm[:, :g.nwin * 64])
+    assert (wm[:, g.nwin * 64:] == -1).all()
+    assert g.G == ((h + pad_b) // 4) * ((w + pad_r) // 4) and g.R % 64 == 0
+
+
+def test_hidden_permutation_matches_fold():
+    """Position-major hidden layout (p*C + c) is a pure re-indexing of nn.Fold's (c*P + p)."""
+    model, _ = _small_model()
+    perm = model.net._perm_hidden(40)
+    hid = torch.randn(1, 35, 1960)  # 5x7 tokens
+    ref = F.fold(hid.transpose(1, 2), (15, 21), (7, 7), stride=3, padding=3)
+    hp = hid[:, :, perm].reshape(1, 5, 7, 49, 40)
+    img = torch.zeros(1, 40, 15, 21)
+    for ty in range(5):
+        for tx in range(7):
+            for p in range(49):
+                y, x = ty * 3 + p // 7 - 3, tx * 3 + p % 7 - 3
+                if 0 <= y < 15 and 0 <= x < 21:
+                    img[0, :, y, x] += hp[0, ty, tx, p]
+    assert torch.allclose(img, ref, atol=1e-5)
