@@ -64,6 +64,101 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
+// Epilogue parameters hoisted into registers once per CTA.
+struct EpiArgs {
+  float* out_f32;
+  __nv_bfloat16* out_hi;
+  const float* aux;
+  long long out_plane, os_c;
+  float alpha;
+  int act, aux_mode, vec_ok, N;
+};
+
+template <int NC>
+__device__ __forceinline__ void epi_chunk(const EpiArgs& e, const uint32_t (&raw)[NC], const float* sb, long long off,
+                                          int col0) {
+  float v[NC];
+#pragma unroll
+  for (int q = 0; q < NC / 4; ++q) {
+    const float4 b = *reinterpret_cast<const float4*>(sb + 4 * q);
+    v[4 * q] = fmaf(__uint_as_float(raw[4 * q]), e.alpha, b.x);
+    v[4 * q + 1] = fmaf(__uint_as_float(raw[4 * q + 1]), e.alpha, b.y);
+    v[4 * q + 2] = fmaf(__uint_as_float(raw[4 * q + 2]), e.alpha, b.z);
+    v[4 * q + 3] = fmaf(__uint_as_float(raw[4 * q + 3]), e.alpha, b.w);
+  }
+  if (e.act == FGT_ACT_LEAKY02) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
+  } else if (e.act == FGT_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) v[j] = fmaxf(v[j], 0.f);
+  } else if (e.act == FGT_ACT_SIGMOID) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
+  } else if (e.act == FGT_ACT_TANH) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) v[j] = tanhf(v[j]);
+  }
+  if (e.vec_ok && col0 + NC <= e.N) {
+    const long long o = off + col0;
+    if (e.aux_mode == FGT_AUX_ADD) {
+      const float4* ap = reinterpret_cast<const float4*>(e.aux + o);
+#pragma unroll
+      for (int q = 0; q < NC / 4; ++q) {
+        const float4 a = __ldg(ap + q);
+        v[4 * q] += a.x; v[4 * q + 1] += a.y; v[4 * q + 2] += a.z; v[4 * q + 3] += a.w;
+      }
+    } else if (e.aux_mode == FGT_AUX_MUL) {
+      const float4* ap = reinterpret_cast<const float4*>(e.aux + o);
+#pragma unroll
+      for (int q = 0; q < NC / 4; ++q) {
+        const float4 a = __ldg(ap + q);
+        v[4 * q] *= a.x; v[4 * q + 1] *= a.y; v[4 * q + 2] *= a.z; v[4 * q + 3] *= a.w;
+      }
+    }
+    if (e.out_f32) {
+      float4* op = reinterpret_cast<float4*>(e.out_f32 + o);
+#pragma unroll
+      for (int q = 0; q < NC / 4; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+    if (e.out_hi) {
+      uint4* hp = reinterpret_cast<uint4*>(e.out_hi + o);
+      uint4* lp = reinterpret_cast<uint4*>(e.out_hi + e.out_plane + o);
+#pragma unroll
+      for (int q = 0; q < NC / 8; ++q) {
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          __nv_bfloat16 h0, l0, h1, l1;
+          split_bf16(v[8 * q + 2 * t], h0, l0);
+          split_bf16(v[8 * q + 2 * t + 1], h1, l1);
+          hw[t] = pack_bf16x2(h0, h1);
+          lw[t] = pack_bf16x2(l0, l1);
+        }
+        hp[q] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        lp[q] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      }
+    }
+  } else {
+    // generic path: strided channel stores (transposed / NCHW outputs) and N tails
+    for (int j = 0; j < NC; ++j) {
+      if (col0 + j < e.N) {
+        const long long o = off + static_cast<long long>(col0 + j) * e.os_c;
+        float x = v[j];
+        if (e.aux_mode == FGT_AUX_ADD) x += __ldg(e.aux + o);
+        else if (e.aux_mode == FGT_AUX_MUL) x *= __ldg(e.aux + o);
+        if (e.out_f32) e.out_f32[o] = x;
+        if (e.out_hi) {
+          __nv_bfloat16 h, l;
+          split_bf16(x, h, l);
+          e.out_hi[o] = h;
+          e.out_hi[e.out_plane + o] = l;
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms.
@@ -80,6 +175,8 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
   auto accf_bar = [&](int b) { return bar_base + 8u * (2 * p.stages + b); };
   auto acce_bar = [&](int b) { return bar_base + 8u * (2 * p.stages + 2 + b); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * p.stages + 4);
+  // per-tile bias slice staged in smem (2 buffers x 256 floats), after the 256-byte barrier block
+  float* sbias_base = reinterpret_cast<float*>(smem_raw + (bar_base - smem_u32(smem_raw)) + 256);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -184,6 +281,10 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     // ------------------------------------------------------------ epilogue (warps 2..5)
     const int quarter = warp & 3;  // TMEM lane quarter this warp may read
     const int r = quarter * 32 + lane;
+    EpiArgs ep;
+    ep.out_f32 = p.out_f32; ep.out_hi = p.out_hi; ep.aux = p.aux; ep.out_plane = p.out_plane; ep.os_c = p.os_c;
+    ep.alpha = p.alpha; ep.act = p.act; ep.aux_mode = p.aux_mode; ep.vec_ok = p.vec_ok; ep.N = p.N;
+    const int e_bn = p.bn, e_bn_p2 = p.bn_p2, e_N = p.N;
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
       const int buf = lt & 1;
@@ -222,78 +323,29 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
         off = z * p.os_z + oy * p.os_y + ox * p.os_x;
       }
 
+      // stage this tile's bias slice (zeros beyond N / without bias); 128 epilogue threads cooperate
+      float* sbias = sbias_base + buf * 256;
+      for (int c = threadIdx.x - 64; c < p.bn; c += 128)
+        sbias[c] = (p.bias && n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.f;
+      asm volatile("bar.sync 1, 128;\n" ::: "memory");
+
       mbar_wait(accf_bar(buf), aph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                             static_cast<uint32_t>(buf * p.bn_p2);
-      for (int c0 = 0; c0 < p.bn; c0 += 16) {
-        uint32_t raw[16];
-        tmem_ld16(t_row + c0, raw);
-        tmem_ld_wait();
-        const int col0 = n0 + c0;
-        if (!valid || col0 >= p.N) continue;
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float x = __uint_as_float(raw[j]) * p.alpha;
-          if (p.bias && col0 + j < p.N) x += __ldg(p.bias + col0 + j);
-          v[j] = apply_act(x, p.act);
+                             static_cast<uint32_t>(buf * e_bn_p2);
+      if ((e_bn & 31) == 0) {
+        for (int c0 = 0; c0 < e_bn; c0 += 32) {
+          uint32_t raw[32];
+          tmem_ld32(t_row + c0, raw);
+          tmem_ld_wait();
+          if (valid && n0 + c0 < e_N) epi_chunk<32>(ep, raw, sbias + c0, off, n0 + c0);
         }
-        const bool full16 = col0 + 16 <= p.N;
-        if (p.vec_ok && full16) {
-          const long long o = off + col0;
-          if (p.aux_mode != FGT_AUX_NONE) {
-            const float4* ap = reinterpret_cast<const float4*>(p.aux + o);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 a = __ldg(ap + q);
-              if (p.aux_mode == FGT_AUX_ADD) {
-                v[4 * q] += a.x; v[4 * q + 1] += a.y; v[4 * q + 2] += a.z; v[4 * q + 3] += a.w;
-              } else {
-                v[4 * q] *= a.x; v[4 * q + 1] *= a.y; v[4 * q + 2] *= a.z; v[4 * q + 3] *= a.w;
-              }
-            }
-          }
-          if (p.out_f32) {
-            float4* op = reinterpret_cast<float4*>(p.out_f32 + o);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          }
-          if (p.out_hi) {
-            uint32_t hw[8], lw[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              __nv_bfloat16 h0, l0, h1, l1;
-              split_bf16(v[2 * q], h0, l0);
-              split_bf16(v[2 * q + 1], h1, l1);
-              hw[q] = pack_bf16x2(h0, h1);
-              lw[q] = pack_bf16x2(l0, l1);
-            }
-            uint4* hp = reinterpret_cast<uint4*>(p.out_hi + o);
-            uint4* lp = reinterpret_cast<uint4*>(p.out_hi + p.out_plane + o);
-            hp[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            hp[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-            lp[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-            lp[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (col0 + j < p.N) {
-              const long long o = off + static_cast<long long>(col0 + j) * p.os_c;
-              float x = v[j];
-              if (p.aux_mode == FGT_AUX_ADD) x += __ldg(p.aux + o);
-              else if (p.aux_mode == FGT_AUX_MUL) x *= __ldg(p.aux + o);
-              if (p.out_f32) p.out_f32[o] = x;
-              if (p.out_hi) {
-                __nv_bfloat16 h, l;
-                split_bf16(x, h, l);
-                p.out_hi[o] = h;
-                p.out_hi[p.out_plane + o] = l;
-              }
-            }
-          }
+      } else {
+        for (int c0 = 0; c0 < e_bn; c0 += 16) {
+          uint32_t raw[16];
+          tmem_ld16(t_row + c0, raw);
+          tmem_ld_wait();
+          if (valid && n0 + c0 < e_N) epi_chunk<16>(ep, raw, sbias + c0, off, n0 + c0);
         }
       }
       tc_fence_before();
@@ -438,11 +490,11 @@ int gemm_tc_launch(const FgtGemmDesc& d, cudaStream_t stream) {
                  : 0;
 
   const uint32_t stage_bytes = 2u * kAPlaneBytes + 2u * static_cast<uint32_t>(d.bn) * 128u;
-  int stages = static_cast<int>((227u * 1024u - 2048u) / stage_bytes);
+  int stages = static_cast<int>((227u * 1024u - 1024u - 4096u) / stage_bytes);
   if (stages > 6) stages = 6;
   FGT_REQUIRE(stages >= 2, FGT_ERR_ARG, "gemm_tc: tile too large for shared memory");
   p.stages = stages;
-  const size_t smem = static_cast<size_t>(stages) * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+  const size_t smem = static_cast<size_t>(stages) * stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + 2048 /*bias*/;
 
   static bool attr_set = false;
   if (!attr_set) {

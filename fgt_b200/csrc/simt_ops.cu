@@ -50,6 +50,61 @@ __global__ void pack_nchw_kernel(const float* __restrict__ s0, int c0, const flo
 }
 
 // ------------------------------------------------------------------------------------------
+// im2col for the tiny-channel first layers (4->64 3x3 s2, 2->64 5x5 after ReplicationPad2d(2),
+// model.py:34,207-208): gathers the k x k neighbourhood of NCHW fp32 inputs (two sources concatenated
+// on C) into one 64-channel NHWC split row per output pixel, channel = (ky*k + kx)*cin + c. The
+// convolution then is a single K=64 GEMM instead of k*k zero-padded 64-channel taps.
+// ------------------------------------------------------------------------------------------
+__global__ void im2col_nchw_kernel(const float* __restrict__ s0, int c0, const float* __restrict__ s1, int c1,
+                                   int n, int H, int W, int k, int stride, int pad, int replicate, int OH, int OW,
+                                   int cpad, __nv_bfloat16* __restrict__ hi, long long plane) {
+  const int cin = c0 + c1;
+  const int groups = cpad / 8;
+  const long long total = static_cast<long long>(n) * OH * OW * groups;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % groups);
+    const long long pix = i / groups;
+    const int ox = static_cast<int>(pix % OW);
+    const int oy = static_cast<int>((pix / OW) % OH);
+    const int b = static_cast<int>(pix / (static_cast<long long>(OW) * OH));
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ch = g * 8 + j;
+      float val = 0.f;
+      if (ch < k * k * cin) {
+        const int tap = ch / cin, c = ch - tap * cin;
+        int y = oy * stride + tap / k - pad, x = ox * stride + tap % k - pad;
+        bool ok = true;
+        if (replicate) {
+          y = min(max(y, 0), H - 1);
+          x = min(max(x, 0), W - 1);
+        } else {
+          ok = y >= 0 && y < H && x >= 0 && x < W;
+        }
+        if (ok)
+          val = (c < c0) ? __ldg(s0 + ((static_cast<long long>(b) * c0 + c) * H + y) * W + x)
+                         : __ldg(s1 + ((static_cast<long long>(b) * c1 + (c - c0)) * H + y) * W + x);
+      }
+      v[j] = val;
+    }
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split_bf16(v[2 * t], h0, l0);
+      split_bf16(v[2 * t + 1], h1, l1);
+      hw[t] = pack_bf16x2(h0, h1);
+      lw[t] = pack_bf16x2(l0, l1);
+    }
+    const long long o = pix * cpad + g * 8;
+    *reinterpret_cast<uint4*>(hi + o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4*>(hi + plane + o) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // rownorm: per-row LayerNorm statistics (no affine: gamma/beta are folded into the consuming
 // Linear) over the concatenation of up to two fp32 sources; optional gather map (dest row ->
 // source row, <0 = write zeros: the reference's zero padding happens before/after LN in a way that
@@ -311,6 +366,20 @@ extern "C" int fgt_pack_nchw(const float* src0, int c0, const float* src1, int c
   const long long total = static_cast<long long>(n) * (H + 2 * pad) * (W + 2 * pad);
   pack_nchw_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       src0, c0, src1, c1, n, H, W, pad, cpad, reinterpret_cast<__nv_bfloat16*>(out_hi), out_plane);
+  FGT_CUDA(cudaGetLastError());
+  return FGT_OK;
+}
+
+extern "C" int fgt_im2col_nchw(const float* src0, int c0, const float* src1, int c1, int n, int H, int W, int k,
+                               int stride, int pad, int replicate, int OH, int OW, int cpad, void* out_hi,
+                               long long out_plane, fgt_stream_t stream) {
+  FGT_REQUIRE(src0 && c0 >= 1 && (c1 == 0 || src1) && cpad % 8 == 0 && k * k * (c0 + c1) <= cpad && k >= 1 &&
+                  stride >= 1,
+              FGT_ERR_ARG, "im2col_nchw: k=%d cin=%d cpad=%d", k, c0 + c1, cpad);
+  const long long total = static_cast<long long>(n) * OH * OW * (cpad / 8);
+  im2col_nchw_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src0, c0, src1, c1, n, H, W, k, stride, pad, replicate, OH, OW, cpad, reinterpret_cast<__nv_bfloat16*>(out_hi),
+      out_plane);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;
 }

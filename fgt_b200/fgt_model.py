@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import lib
-from .packing import fold_layernorm, pack_weight
+from .packing import fold_layernorm, pack_weight, pack_weight_im2col
 
 LN_EPS = 1e-5
 
@@ -228,19 +228,23 @@ class FGT(nn.Module):
         P = {}
 
         def put(name, w, b, segs=None):
-            P[name] = dict(w=pack_weight(w, segs).to(dev), b=b.float().contiguous().to(dev), N=w.shape[0])
+            P[name] = dict(w=pack_weight(w, segs).to(dev), b=b.float().contiguous().to(dev), N=w.shape[0], name=name)
 
         def conv(name, key, segs=None):
             put(name, sd[key + ".weight"], sd[key + ".bias"], segs)
 
         enc = "frame_endoder.layers."
-        for i in (0, 2, 4, 6, 8):
+        for i in (2, 4, 6, 8):
             conv(f"enc{i}", enc + str(i))
+        # tiny-channel first layers consume im2col rows (fgt_im2col_nchw): one K=64 GEMM each
+        for name, key in (("enc0", enc + "0"), ("fenc1", "flow_encoder.1.featureConv")):
+            P[name] = dict(w=pack_weight_im2col(sd[key + ".weight"]).to(dev), b=sd[key + ".bias"].contiguous().to(dev),
+                           N=sd[key + ".weight"].shape[0], name=name)
         conv("enc10", enc + "10", [128, 192])
         conv("enc12", enc + "12", [64, 128])
         conv("enc14", enc + "14", [32, 48])
         conv("enc16", enc + "16", [256, 256])
-        for i in (1, 2, 3, 4):
+        for i in (2, 3, 4):
             conv(f"fenc{i}", f"flow_encoder.{i}.featureConv")
         conv("patch2vec", "patch2vec")
         conv("f_patch2vec", "f_patch2vec")
@@ -380,12 +384,12 @@ class FGT(nn.Module):
             strides = dict(os_z=oh * ow * N, os_y=ow * N, os_x=N, os_c=1)
         lib.gemm_tc(segs, wp["w"], N, kx=k, ky=k, stride=stride, pad_x=pad, pad_y=pad, groups=groups, out_w=ow,
                     out_h=oh, out_z=n, box_w=bw, box_h=bh, bn=_pick_bn(N // groups, groups), bias=wp["b"], act=act,
-                    out_f32=out_f32, out_split=out_split, **strides)
+                    out_f32=out_f32, out_split=out_split, tag=wp["name"], **strides)
         return oh, ow
 
     @staticmethod
     def _linear(segs, wp, rows, **kw):
-        lib.gemm_tc(segs, wp["w"], wp["N"], out_w=rows, bn=_pick_bn(wp["N"], 1), bias=wp["b"], **kw)
+        lib.gemm_tc(segs, wp["w"], wp["N"], out_w=rows, bn=_pick_bn(wp["N"], 1), bias=wp["b"], tag=wp["name"], **kw)
 
     def _ffn(self, g, P, name, x, xs, dev):
         """x += FusionFeedForward(LN(x)) (ffn_base.py:53-77, model.py:128-129 / 147-148)."""
@@ -418,7 +422,7 @@ class FGT(nn.Module):
         lib.attention(qk, qk, vt, att, batches=g.zones, heads=self.heads, Lq=g.Lz, Lk=g.Lz, q_ld=2 * d, k_ld=2 * d,
                       vt_ld=g.Lzp, out_ld=d, q_batch_stride=g.Lz * 2 * d, k_batch_stride=g.Lz * 2 * d,
                       vt_batch_stride=d * g.Lzp, out_batch_stride=g.Lz * d, scale=1.0 / math.sqrt(d // self.heads),
-                      k_off=d)
+                      k_off=d, tag=name)
         self._linear([lib.ASeg(att, d, rows_z)], P[name + ".o"], rows_z, rowmap=g.zone_map, aux=x,
                      aux_mode=lib.AUX_ADD, out_f32=x)
         self._ffn(g, P, name, x, xs, dev)
@@ -457,7 +461,7 @@ class FGT(nn.Module):
         lib.attention(qk, qk, vt, att, batches=bt, heads=self.heads, Lq=nl, Lk=g.R, Lk_rows=g.R, q_ld=2 * d,
                       k_ld=2 * d, vt_ld=g.R, out_ld=d, q_batch_stride=g.R * 2 * d, k_batch_stride=g.R * 2 * d,
                       vt_batch_stride=d * g.R, out_batch_stride=nl * d, scale=1.0 / math.sqrt(d // self.heads),
-                      mode=1, glob_start=nl, glob_count=g.G, k_off=d)
+                      mode=1, glob_start=nl, glob_count=g.G, k_off=d, tag=name)
         self._linear([lib.ASeg(att, d, bt * nl)], P[name + ".o"], bt * nl, rowmap=g.win_map, aux=x,
                      aux_mode=lib.AUX_ADD, out_f32=x)
         self._ffn(g, P, name, x, xs, dev)
@@ -478,8 +482,8 @@ class FGT(nn.Module):
         H2, W2, OH, OW = H // 2, W // 2, g.OH, g.OW
 
         # ---- frame encoder (model.py:53-66)
-        in8 = B("in8", (bt, H, W, 8), split=True)
-        lib.pack_nchw(frames, mk, in8)
+        incol = B("in_col", (bt, H2, W2, 64), split=True)
+        lib.im2col_nchw(frames, mk, incol, k=3, stride=2, pad=1, replicate=False, OH=H2, OW=W2, tag="enc0")
         e0 = B("e0", (bt, H2, W2, 64), split=True)
         e2 = B("e2", (bt, H2, W2, 64), split=True)
         e4 = B("e4", (bt, OH, OW, 128), split=True)
@@ -490,7 +494,7 @@ class FGT(nn.Module):
         e14 = B("e14", (bt, OH, OW, 256), split=True)
         enc = B("enc", (bt, OH, OW, 128), split=True)
         enc_f = B("enc_f", (bt, OH, OW, 128))
-        self._conv(in8, 8, bt, H, W, P["enc0"], 3, stride=2, out_split=e0)
+        self._linear([lib.ASeg(incol, 64, bt * H2 * W2)], P["enc0"], bt * H2 * W2, act=lib.ACT_LEAKY02, out_split=e0)
         self._conv(e0, 64, bt, H2, W2, P["enc2"], 3, out_split=e2)
         self._conv(e2, 64, bt, H2, W2, P["enc4"], 3, stride=2, out_split=e4)
         self._conv(e4, 128, bt, OH, OW, P["enc6"], 3, out_split=x0)
@@ -504,13 +508,13 @@ class FGT(nn.Module):
         self._conv(x0, 256, bt, OH, OW, P["enc16"], 3, out_split=enc, out_f32=enc_f, extra_seg=(e14, 256), groups=1,
                    seg_counts=[256, 256])
         # ---- flow encoder (model.py:206-212)
-        fin = B("fin8", (bt, H + 4, W + 4, 8), split=True)
-        lib.pack_nchw(fl, None, fin, pad=2)
+        fcol = B("f_col", (bt, H, W, 64), split=True)
+        lib.im2col_nchw(fl, None, fcol, k=5, stride=1, pad=2, replicate=True, OH=H, OW=W, tag="fenc1")
         f1 = B("f1", (bt, H, W, 64), split=True)
         f2 = B("f2", (bt, H2, W2, 128), split=True)
         f3 = B("f3", (bt, H2, W2, 128), split=True)
         f4 = B("f4", (bt, OH, OW, 128), split=True)
-        self._conv(fin, 8, bt, H + 4, W + 4, P["fenc1"], 5, pad=0, out_split=f1)
+        self._linear([lib.ASeg(fcol, 64, bt * H * W)], P["fenc1"], bt * H * W, act=lib.ACT_LEAKY02, out_split=f1)
         self._conv(f1, 64, bt, H, W, P["fenc2"], 3, stride=2, out_split=f2)
         self._conv(f2, 128, bt, H2, W2, P["fenc3"], 3, out_split=f3)
         self._conv(f3, 128, bt, H2, W2, P["fenc4"], 3, stride=2, out_split=f4)

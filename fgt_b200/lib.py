@@ -73,6 +73,8 @@ def load():
     lib.fgt_attention.restype = ctypes.c_int
     ci, cf, cll = ctypes.c_int, ctypes.c_float, _c_ll
     lib.fgt_pack_nchw.argtypes = [_c_p, ci, _c_p, ci, ci, ci, ci, ci, ci, _c_p, cll, _c_p]
+    lib.fgt_im2col_nchw.argtypes = [_c_p, ci, _c_p, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, _c_p, cll, _c_p]
+    lib.fgt_im2col_nchw.restype = ctypes.c_int
     lib.fgt_rownorm.argtypes = [_c_p, ci, ci, _c_p, ci, ci, _c_p, ci, cll, ci, ci, _c_p, _c_p, _c_p, cll, cf, _c_p]
     lib.fgt_dwpool.argtypes = [_c_p, ci, _c_p, ci, ci, ci, ci, ci, ci, ci, _c_p, _c_p, _c_p, _c_p]
     lib.fgt_dwconv3x3_res.argtypes = [_c_p, ci, ci, ci, ci, _c_p, _c_p, _c_p, _c_p, cll, _c_p]
@@ -90,6 +92,45 @@ def check(rc, what):
     if rc != 0:
         msg = load().fgt_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+    COUNTERS["launches"] += 1
+
+
+# Kernel-launch counter (bench.py's "gpu_launches") and optional per-launch CUDA-event profiler.
+COUNTERS = {"launches": 0}
+_profile = None  # list of (kernel, tag, flops, bytes, ev_start, ev_end) when enabled
+
+
+def profile_start():
+    global _profile
+    _profile = []
+
+
+def profile_stop():
+    """Returns [(kernel, tag, algorithmic_flops, algorithmic_bytes, milliseconds)]; syncs the device."""
+    global _profile
+    recs, _profile = _profile, None
+    torch.cuda.synchronize()
+    return [(k, t, fl, by, e0.elapsed_time(e1)) for (k, t, fl, by, e0, e1) in recs]
+
+
+class _Prof:
+    """Brackets one C-ABI launch with CUDA events on the launching stream when profiling is on."""
+
+    def __init__(self, kernel, tag, flops=0.0, nbytes=0.0):
+        self.meta = (kernel, tag, float(flops), float(nbytes))
+
+    def __enter__(self):
+        if _profile is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _profile is not None and exc[0] is None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _profile.append(self.meta + (self.e0, e1))
+        return False
 
 
 def stream_ptr():
@@ -143,11 +184,12 @@ class ASeg:
 def gemm_tc(segs, w_split, N, *, kx=1, ky=1, kz=1, stride=1, dil=1, pad_x=0, pad_y=0, pad_z=0, groups=1,
             out_w, out_h=1, out_z=1, box_w=128, box_h=1, bn=128, bias=None, alpha=1.0, act=ACT_NONE,
             aux=None, aux_mode=AUX_NONE, out_f32=None, out_split=None, out_elem_offset=0,
-            os_z=0, os_y=0, os_x=None, os_c=1, rowmap=None, lin_batch=0):
+            os_z=0, os_y=0, os_x=None, os_c=1, rowmap=None, lin_batch=0, tag=""):
     """Generic launcher for fgt_gemm_tc. Output strides are in elements; see include/fgt_b200.h."""
     lib = load()
     d = FgtGemmDesc()
     d.num_segs = len(segs)
+    k_real = 0
     for i, s in enumerate(segs):
         a = d.seg[i]
         a.hi = s.split.data_ptr() + 2 * s.elem_offset
@@ -155,6 +197,7 @@ def gemm_tc(segs, w_split, N, *, kx=1, ky=1, kz=1, stride=1, dil=1, pad_x=0, pad
         a.C, a.DX, a.DY, a.DZ = s.C, s.DX, s.DY, s.DZ
         a.sx, a.sy, a.sz = s.sx, s.sy, s.sz
         a.c_base, a.c_per_group, a.c_count = s.c_base, s.c_per_group, s.c_count
+        k_real += s.c_count
     d.kx, d.ky, d.kz, d.stride, d.dil = kx, ky, kz, stride, dil
     d.pad_x, d.pad_y, d.pad_z = pad_x, pad_y, pad_z
     d.w_hi = w_split.data_ptr()
@@ -177,12 +220,18 @@ def gemm_tc(segs, w_split, N, *, kx=1, ky=1, kz=1, stride=1, dil=1, pad_x=0, pad
     d.os_x = N if os_x is None else os_x
     d.rowmap = rowmap.data_ptr() if rowmap is not None else None
     d.lin_batch = lin_batch
-    check(lib.fgt_gemm_tc(ctypes.byref(d), stream_ptr()), "fgt_gemm_tc")
+    # algorithmic work: every valid output position x N x (taps * real input channels), padding excluded
+    m = out_w * out_h * out_z
+    kk = kx * ky * kz * k_real
+    flops = 2.0 * m * N * kk
+    nbytes = 4.0 * (m * k_real * stride * stride + N * kk + m * N)
+    with _Prof("gemm_tc", tag, flops, nbytes):
+        check(lib.fgt_gemm_tc(ctypes.byref(d), stream_ptr()), "fgt_gemm_tc")
 
 
 def attention(q, k, vt, out, *, batches, heads, Lq, Lk, Lk_rows=None, q_ld, k_ld, vt_ld, out_ld,
               q_batch_stride, k_batch_stride, vt_batch_stride, out_batch_stride, scale, mode=0,
-              glob_start=0, glob_count=0, q_off=0, k_off=0):
+              glob_start=0, glob_count=0, q_off=0, k_off=0, tag=""):
     """fgt_attention launcher. q/k/vt/out are split-bf16 tensors; strides in elements; q_off/k_off are
     element offsets into the plane (e.g. when Q and K share one [rows, 2*C] buffer)."""
     lib = load()
@@ -195,56 +244,77 @@ def attention(q, k, vt, out, *, batches, heads, Lq, Lk, Lk_rows=None, q_ld, k_ld
     d.Lq, d.Lk = Lq, Lk
     d.Lk_rows = Lk if Lk_rows is None else Lk_rows
     d.scale, d.mode, d.glob_start, d.glob_count = scale, mode, glob_start, glob_count
-    check(lib.fgt_attention(ctypes.byref(d), stream_ptr()), "fgt_attention")
+    keys = Lk if mode == 0 else 64 + glob_count
+    flops = 4.0 * batches * heads * Lq * keys * 128
+    nbytes = 4.0 * batches * heads * 128 * (2 * Lq + 2 * (Lk if mode == 0 else d.Lk_rows))
+    with _Prof("flash", tag, flops, nbytes):
+        check(lib.fgt_attention(ctypes.byref(d), stream_ptr()), "fgt_attention")
 
 
 def _dp(t):
     return t.data_ptr() if t is not None else None
 
 
-def pack_nchw(src0, src1, out_split, pad=0):
+def pack_nchw(src0, src1, out_split, pad=0, tag=""):
     """[n,c0,H,W] (+ [n,c1,H,W]) fp32 -> NHWC split [2, n, H+2p, W+2p, cpad] with replication pad."""
     n, c0, H, W = src0.shape
     c1 = src1.shape[1] if src1 is not None else 0
     cpad = out_split.shape[-1]
-    check(load().fgt_pack_nchw(_dp(src0), c0, _dp(src1), c1, n, H, W, pad, cpad, _dp(out_split),
-                               plane_elems(out_split), stream_ptr()), "fgt_pack_nchw")
+    with _Prof("pack_nchw", tag, 0, 4.0 * n * (c0 + c1) * H * W + 4.0 * out_split[0].numel()):
+        check(load().fgt_pack_nchw(_dp(src0), c0, _dp(src1), c1, n, H, W, pad, cpad, _dp(out_split),
+                                   plane_elems(out_split), stream_ptr()), "fgt_pack_nchw")
+
+
+def im2col_nchw(src0, src1, out_split, *, k, stride, pad, replicate, OH, OW, tag=""):
+    """[n,c0,H,W] (+[n,c1,H,W]) fp32 -> [2, n, OH, OW, cpad] split rows of k*k*cin gathered inputs."""
+    n, c0, H, W = src0.shape
+    c1 = src1.shape[1] if src1 is not None else 0
+    cpad = out_split.shape[-1]
+    with _Prof("im2col_nchw", tag, 0, 4.0 * n * (c0 + c1) * H * W + 4.0 * out_split[0].numel()):
+        check(load().fgt_im2col_nchw(_dp(src0), c0, _dp(src1), c1, n, H, W, k, stride, pad, 1 if replicate else 0,
+                                     OH, OW, cpad, _dp(out_split), plane_elems(out_split), stream_ptr()),
+              "fgt_im2col_nchw")
 
 
 def rownorm(a, b, out_split, *, gather=None, rows_per_batch, total_rows, dst_batch_rows, dst_row0=0, eps=1e-5,
-            gamma=None, beta=None):
+            gamma=None, beta=None, tag=""):
     ca, lda = a.shape[-1], a.shape[-1]
     cb, ldb = (b.shape[-1], b.shape[-1]) if b is not None else (0, 0)
-    check(load().fgt_rownorm(_dp(a), ca, lda, _dp(b), cb, ldb, _dp(gather), rows_per_batch, total_rows,
-                             dst_batch_rows, dst_row0, _dp(gamma), _dp(beta), _dp(out_split), plane_elems(out_split),
-                             eps, stream_ptr()),
-          "fgt_rownorm")
+    with _Prof("rownorm", tag, 0, 8.0 * total_rows * (ca + cb)):
+        check(load().fgt_rownorm(_dp(a), ca, lda, _dp(b), cb, ldb, _dp(gather), rows_per_batch, total_rows,
+                                 dst_batch_rows, dst_row0, _dp(gamma), _dp(beta), _dp(out_split),
+                                 plane_elems(out_split), eps, stream_ptr()), "fgt_rownorm")
 
 
-def dwpool(a, b, bt, h, w, k, gh, gw, weight, bias, out):
+def dwpool(a, b, bt, h, w, k, gh, gw, weight, bias, out, tag=""):
     ca = a.shape[-1]
     cb = b.shape[-1] if b is not None else 0
-    check(load().fgt_dwpool(_dp(a), ca, _dp(b), cb, bt, h, w, k, gh, gw, _dp(weight), _dp(bias), _dp(out),
-                            stream_ptr()), "fgt_dwpool")
+    with _Prof("dwpool", tag, 0, 4.0 * bt * (h * w + gh * gw) * (ca + cb)):
+        check(load().fgt_dwpool(_dp(a), ca, _dp(b), cb, bt, h, w, k, gh, gw, _dp(weight), _dp(bias), _dp(out),
+                                stream_ptr()), "fgt_dwpool")
 
 
-def dwconv3x3_res(x, bt, h, w, C, weight, bias, out, out_split=None):
-    check(load().fgt_dwconv3x3_res(_dp(x), bt, h, w, C, _dp(weight), _dp(bias), _dp(out), _dp(out_split),
-                                   plane_elems(out_split) if out_split is not None else 0, stream_ptr()),
-          "fgt_dwconv3x3_res")
+def dwconv3x3_res(x, bt, h, w, C, weight, bias, out, out_split=None, tag=""):
+    with _Prof("dwconv3x3_res", tag, 0, 12.0 * bt * h * w * C):
+        check(load().fgt_dwconv3x3_res(_dp(x), bt, h, w, C, _dp(weight), _dp(bias), _dp(out), _dp(out_split),
+                                       plane_elems(out_split) if out_split is not None else 0, stream_ptr()),
+              "fgt_dwconv3x3_res")
 
 
-def fold(hid, bt, th, tw, C, kh, kw, stride, pad, OH, OW, *, normalize, add=None, out=None, out_split=None):
-    check(load().fgt_fold(_dp(hid), bt, th, tw, C, kh, kw, stride, pad, OH, OW, 1 if normalize else 0, _dp(add),
-                          _dp(out), _dp(out_split), plane_elems(out_split) if out_split is not None else 0,
-                          stream_ptr()), "fgt_fold")
+def fold(hid, bt, th, tw, C, kh, kw, stride, pad, OH, OW, *, normalize, add=None, out=None, out_split=None, tag=""):
+    with _Prof("fold", tag, 0, 4.0 * bt * (th * tw * kh * kw * C + OH * OW * C * (2 if add is not None else 1))):
+        check(load().fgt_fold(_dp(hid), bt, th, tw, C, kh, kw, stride, pad, OH, OW, 1 if normalize else 0, _dp(add),
+                              _dp(out), _dp(out_split), plane_elems(out_split) if out_split is not None else 0,
+                              stream_ptr()), "fgt_fold")
 
 
-def unfold(img, bt, th, tw, C, kh, kw, stride, pad, OH, OW, out_split, relu=True):
-    check(load().fgt_unfold(_dp(img), bt, th, tw, C, kh, kw, stride, pad, OH, OW, 1 if relu else 0,
-                            _dp(out_split), plane_elems(out_split), stream_ptr()), "fgt_unfold")
+def unfold(img, bt, th, tw, C, kh, kw, stride, pad, OH, OW, out_split, relu=True, tag=""):
+    with _Prof("unfold", tag, 0, 4.0 * bt * (th * tw * kh * kw * C + OH * OW * C)):
+        check(load().fgt_unfold(_dp(img), bt, th, tw, C, kh, kw, stride, pad, OH, OW, 1 if relu else 0,
+                                _dp(out_split), plane_elems(out_split), stream_ptr()), "fgt_unfold")
 
 
-def upsample2x(in_split, n, H, W, C, out_split):
-    check(load().fgt_upsample2x(_dp(in_split), plane_elems(in_split), n, H, W, C, _dp(out_split),
-                                plane_elems(out_split), stream_ptr()), "fgt_upsample2x")
+def upsample2x(in_split, n, H, W, C, out_split, tag=""):
+    with _Prof("upsample2x", tag, 0, 4.0 * n * H * W * C * 5):
+        check(load().fgt_upsample2x(_dp(in_split), plane_elems(in_split), n, H, W, C, _dp(out_split),
+                                    plane_elems(out_split), stream_ptr()), "fgt_upsample2x")

@@ -52,3 +52,14 @@ def fold_layernorm(weight, bias, gamma, beta):
     w2 = w * g[None, :]
     b2 = w @ b + (bias.detach().double() if bias is not None else 0.0)
     return w2.float(), b2.float()
+
+
+def pack_weight_im2col(w, cpad=KB):
+    """Conv weight [N, cin, k, k] for a layer whose input was gathered by fgt_im2col_nchw:
+    K index = (ky*k + kx)*cin + c, zero-padded to cpad."""
+    w = w.detach().float()
+    n = w.shape[0]
+    flat = w.permute(0, 2, 3, 1).reshape(n, -1)
+    assert flat.shape[1] <= cpad
+    flat = torch.nn.functional.pad(flat, (0, cpad - flat.shape[1]))
+    return to_split(flat.contiguous())

@@ -138,6 +138,15 @@ int fgt_attention(const FgtAttnDesc* desc, fgt_stream_t stream);
 int fgt_pack_nchw(const float* src0, int c0, const float* src1, int c1, int n, int H, int W, int pad, int cpad,
                   void* out_hi, long long out_plane, fgt_stream_t stream);
 
+/* im2col of NCHW fp32 inputs (src0 channels then src1 channels) for the tiny-channel first layers:
+ * output row (n, oy, ox) holds the k x k neighbourhood, channel = (ky*k+kx)*cin + c, zero-padded to
+ * `cpad` (>= k*k*cin) channels; borders are zero (replicate=0) or clamped (replicate=1, i.e.
+ * nn.ReplicationPad2d(pad) followed by an unpadded conv). Feeds fgt_gemm_tc as a K=cpad linear layer.
+ * Replaces the input side of nn.Conv2d at FGT/models/model.py:34 and model.py:207-208. */
+int fgt_im2col_nchw(const float* src0, int c0, const float* src1, int c1, int n, int H, int W, int k, int stride,
+                    int pad, int replicate, int OH, int OW, int cpad, void* out_hi, long long out_plane,
+                    fgt_stream_t stream);
+
 /* LayerNorm over the channel concatenation [a ; b] of fp32 rows. gamma/beta may be NULL (statistics
  * only: the affine is then folded into the consuming Linear at weight-pack time). Destination row of work item d is
  * (d / rows_per_batch) * dst_batch_rows + dst_row0 + d % rows_per_batch; its source row is
