@@ -86,9 +86,26 @@ __device__ __forceinline__ void epi_chunk(const EpiArgs& e, const uint32_t (&raw
     v[4 * q + 2] = fmaf(__uint_as_float(raw[4 * q + 2]), e.alpha, b.z);
     v[4 * q + 3] = fmaf(__uint_as_float(raw[4 * q + 3]), e.alpha, b.w);
   }
+  const bool vec = e.vec_ok && col0 + NC <= e.N;
+  if (e.aux_mode == FGT_AUX_ADD_PRE) {  // residual added BEFORE the activation (LAFC edge head)
+    if (vec) {
+      const float4* ap = reinterpret_cast<const float4*>(e.aux + off + col0);
+#pragma unroll
+      for (int q = 0; q < NC / 4; ++q) {
+        const float4 a = __ldg(ap + q);
+        v[4 * q] += a.x; v[4 * q + 1] += a.y; v[4 * q + 2] += a.z; v[4 * q + 3] += a.w;
+      }
+    } else {
+      for (int j = 0; j < NC; ++j)
+        if (col0 + j < e.N) v[j] += __ldg(e.aux + off + static_cast<long long>(col0 + j) * e.os_c);
+    }
+  }
   if (e.act == FGT_ACT_LEAKY02) {
 #pragma unroll
     for (int j = 0; j < NC; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
+  } else if (e.act == FGT_ACT_LEAKY001) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) v[j] = v[j] > 0.f ? v[j] : 0.01f * v[j];
   } else if (e.act == FGT_ACT_RELU) {
 #pragma unroll
     for (int j = 0; j < NC; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -99,7 +116,7 @@ __device__ __forceinline__ void epi_chunk(const EpiArgs& e, const uint32_t (&raw
 #pragma unroll
     for (int j = 0; j < NC; ++j) v[j] = tanhf(v[j]);
   }
-  if (e.vec_ok && col0 + NC <= e.N) {
+  if (vec) {
     const long long o = off + col0;
     if (e.aux_mode == FGT_AUX_ADD) {
       const float4* ap = reinterpret_cast<const float4*>(e.aux + o);

@@ -112,12 +112,14 @@ def make_state_dict(shapes, seed=0, regime="scaled"):
                 gain = 0.5  # keep tanh out of saturation
             elif "vec2patch" in key:
                 gain = 0.25
+            if regime == "kaiming":  # LAFC's reference init (kaiming_normal fan_in, LAFC/models/BaseNetwork.py)
+                gain = math.sqrt(2.0)
             std = 0.02 if regime == "default" else gain / math.sqrt(fan_in)
             sd[key] = torch.randn(shape, generator=g) * std
         elif key.endswith(".weight"):  # LayerNorm gamma
             sd[key] = torch.ones(shape) if regime == "default" else 1.0 + 0.2 * torch.randn(shape, generator=g)
         else:  # biases / LN beta
-            if regime == "default":
+            if regime in ("default", "kaiming"):
                 sd[key] = torch.zeros(shape)
             else:
                 sd[key] = (0.1 if is_norm else 0.05) * torch.randn(shape, generator=g)
@@ -158,3 +160,66 @@ def fgt_inputs(seed=0, t=10, H=240, W=432, b=1):
     mx = flows.amax(dim=(2, 3), keepdim=True)
     flows = (flows / mx).reshape(b, t, 2, H, W)
     return frames * (1 - masks), flows, masks
+
+
+# ----------------------------------------------------------------------------------------------
+# LAFC (flow completion)
+# ----------------------------------------------------------------------------------------------
+CFG_LAFC = dict(num_flows=3, flow_interval=3, cnum=48, in_channel=3, PASSMASK=1, use_residual=1, resBlocks=1,
+                use_bias=1, conv_type='vanilla', init_weights=1, model='lafc')
+
+
+def lafc_param_shapes(cfg=CFG_LAFC):
+    """state_dict contract of LAFC.models.lafc.Model (/root/reference/LAFC/models/lafc.py:18-82)."""
+    c, T = cfg['cnum'], cfg['num_flows']
+    s = {}
+
+    def c3(name, co, ci, kt, k):
+        s[name + ".featureConv.weight"] = (co, ci, kt, k, k)
+        s[name + ".featureConv.bias"] = (co,)
+
+    def c2(name, co, ci, k):
+        s[name + ".featureConv.weight"] = (co, ci, k, k)
+        s[name + ".featureConv.bias"] = (co,)
+
+    def p3d(name, ci, co, k):
+        c3(name + ".conv1", co, ci, 1, k)
+        c3(name + ".conv2", co, co, 3, 1)
+
+    p3d("encoder2.1", cfg['in_channel'], c, 5)
+    p3d("encoder2.2", c, 2 * c, 3)
+    p3d("encoder4.0", 2 * c, 2 * c, 3)
+    p3d("encoder4.1", 2 * c, 4 * c, 3)
+    p3d("res_blocks.0", 4 * c, 4 * c, 3)
+    c3("condense2", 2 * c, 2 * c, T, 1)
+    c3("condense4_pre", 4 * c, 4 * c, T, 1)
+    c3("condense4_post", 4 * c, 4 * c, T, 1)
+    for i in range(4):
+        c2(f"middle.{i}", 4 * c, 4 * c, 3)
+    c2("decoder2.0.conv", 2 * c, 8 * c, 3)
+    c2("decoder2.1", 2 * c, 2 * c, 3)
+    c2("decoder2.2", 2 * c, 2 * c, 3)
+    c2("decoder.0.conv", c, 4 * c, 3)
+    c2("decoder.1", c // 2, c, 3)
+    c2("decoder.2", 2, c // 2, 3)
+    c2("edgeDetector.projection", 16, 2, 3)
+    c2("edgeDetector.mid_layer_1", 16, 16, 3)
+    c2("edgeDetector.mid_layer_2", 16, 16, 3)
+    c2("edgeDetector.out_layer", 1, 16, 1)
+    return {"net." + k: v for k, v in s.items()}
+
+
+def lafc_inputs(seed=0, T=3, H=240, W=432, b=1):
+    """Diffused candidate flows (pixels) and hole masks shaped like complete_flow's call
+    (/root/reference/tool/video_inpainting.py:369-378): flows [b,2,T,H,W], masks [b,1,T,H,W]."""
+    g = torch.Generator().manual_seed(seed)
+    flows = _smooth(torch.randn(b * T, 2, H, W, generator=g), k=21) * 60.0
+    masks = torch.zeros(b, 1, T, H, W)
+    for bi in range(b):
+        for ti in range(T):
+            r = torch.rand(4, generator=g)
+            hh, ww = int(H * (0.2 + 0.3 * r[0].item())), int(W * (0.2 + 0.3 * r[1].item()))
+            y0, x0 = int((H - hh) * r[2].item()), int((W - ww) * r[3].item())
+            masks[bi, 0, ti, y0:y0 + hh, x0:x0 + ww] = 1.0
+    flows = flows.reshape(b, T, 2, H, W).permute(0, 2, 1, 3, 4).contiguous()
+    return flows, masks

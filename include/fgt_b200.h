@@ -42,8 +42,10 @@ enum {
   FGT_ERR_DEVICE = -3   /* no sm_100 device / driver entry point missing */
 };
 
-enum { FGT_ACT_NONE = 0, FGT_ACT_LEAKY02 = 1, FGT_ACT_RELU = 2, FGT_ACT_SIGMOID = 3, FGT_ACT_TANH = 4 };
-enum { FGT_AUX_NONE = 0, FGT_AUX_ADD = 1, FGT_AUX_MUL = 2 };
+enum { FGT_ACT_NONE = 0, FGT_ACT_LEAKY02 = 1, FGT_ACT_RELU = 2, FGT_ACT_SIGMOID = 3, FGT_ACT_TANH = 4,
+       FGT_ACT_LEAKY001 = 5 /* nn.LeakyReLU() default slope, LAFC/models/lafc.py:138 */ };
+/* aux: out = act(v) + aux | out = act(v) * aux | out = act(v + aux) */
+enum { FGT_AUX_NONE = 0, FGT_AUX_ADD = 1, FGT_AUX_MUL = 2, FGT_AUX_ADD_PRE = 3 };
 
 int fgt_version(void);
 const char* fgt_last_error(void);
@@ -91,7 +93,7 @@ typedef struct {
   float alpha;               /* scale applied to the accumulator before bias */
   int act;                   /* FGT_ACT_* */
   const float* aux;          /* fp32 tensor addressed like the output, or NULL */
-  int aux_mode;              /* FGT_AUX_* : out = aux + v  |  out = aux * v */
+  int aux_mode;              /* FGT_AUX_* */
   float* out_f32;            /* fp32 output or NULL */
   void* out_hi;              /* split-bf16 output (hi plane) or NULL */
   long long out_plane;

@@ -92,7 +92,36 @@ def module_cases():
     print("fgt_modules saved")
 
 
+def lafc_case(name, H, W, regime, seed, sample=None):
+    M = importlib.import_module("LAFC.models.lafc")
+    sd = synth.make_state_dict(synth.lafc_param_shapes(), seed=seed, regime=regime)
+    model = M.Model(synth.CFG_LAFC)
+    model.load_state_dict(sd)
+    fl, mk = synth.lafc_inputs(seed=seed + 1, H=H, W=W)
+    with torch.no_grad():
+        flow, edge = model(fl, mk)
+    meta = dict(H=H, W=W, regime=regime, seed=seed, **VERSIONS)
+    arrs = dict(meta=np.array(repr(meta)), flow_l2=np.float64(flow.double().norm().item()),
+                edge_l2=np.float64(edge.double().norm().item()))
+    if sample is None:
+        arrs["flow"] = flow.numpy().astype(np.float32)
+        arrs["edge"] = edge.numpy().astype(np.float32)
+    else:
+        g = torch.Generator().manual_seed(1234)
+        fi = torch.randperm(flow.numel(), generator=g)[:sample]
+        ei = torch.randperm(edge.numel(), generator=g)[:sample]
+        arrs.update(flow_idx=fi.numpy(), flow_val=flow.reshape(-1)[fi].numpy(), edge_idx=ei.numpy(),
+                    edge_val=edge.reshape(-1)[ei].numpy())
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrs)
+    print(name, "flow std", flow.std().item(), "saved")
+
+
 if __name__ == "__main__":
+    lafc_case("lafc_small_scaled", 64, 96, "scaled", seed=4)
+    lafc_case("lafc_small_kaiming", 64, 96, "kaiming", seed=4)
+    lafc_case("lafc_full", 240, 432, "scaled", seed=5, sample=8192)
+    if "--lafc-only" in sys.argv:
+        sys.exit(0)
     fgt_case("fgt_small_scaled", 64, 96, 3, "scaled", (64, 96), seed=1)
     fgt_case("fgt_small_default", 64, 96, 3, "default", (64, 96), seed=1)
     fgt_case("fgt_runtime_geo", 72, 100, 2, "scaled", (64, 96), seed=2)
