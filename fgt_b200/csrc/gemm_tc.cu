@@ -48,6 +48,7 @@ struct GemmParams {
   __nv_bfloat16* out_hi;
   long long out_plane;
   const float* aux;
+  const float* aux2;
   int aux_mode;
   const float* bias;
   int act;
@@ -69,6 +70,7 @@ struct EpiArgs {
   float* out_f32;
   __nv_bfloat16* out_hi;
   const float* aux;
+  const float* aux2;
   long long out_plane, os_c;
   float alpha;
   int act, aux_mode, vec_ok, N;
@@ -132,6 +134,26 @@ __device__ __forceinline__ void epi_chunk(const EpiArgs& e, const uint32_t (&raw
         const float4 a = __ldg(ap + q);
         v[4 * q] *= a.x; v[4 * q + 1] *= a.y; v[4 * q + 2] *= a.z; v[4 * q + 3] *= a.w;
       }
+    } else if (e.aux_mode == FGT_AUX_ADD_RELU) {
+      const float4* ap = reinterpret_cast<const float4*>(e.aux + o);
+#pragma unroll
+      for (int q = 0; q < NC / 4; ++q) {
+        const float4 a = __ldg(ap + q);
+        v[4 * q] = fmaxf(v[4 * q] + a.x, 0.f); v[4 * q + 1] = fmaxf(v[4 * q + 1] + a.y, 0.f);
+        v[4 * q + 2] = fmaxf(v[4 * q + 2] + a.z, 0.f); v[4 * q + 3] = fmaxf(v[4 * q + 3] + a.w, 0.f);
+      }
+    } else if (e.aux_mode == FGT_AUX_GRU) {  // h' = (1 - z) * h + z * q   (aux = h, aux2 = z, v = q)
+      const float4* hp4 = reinterpret_cast<const float4*>(e.aux + o);
+      const float4* zp4 = reinterpret_cast<const float4*>(e.aux2 + o);
+#pragma unroll
+      for (int q = 0; q < NC / 4; ++q) {
+        const float4 h = __ldg(hp4 + q);
+        const float4 z = __ldg(zp4 + q);
+        v[4 * q] = (1.f - z.x) * h.x + z.x * v[4 * q];
+        v[4 * q + 1] = (1.f - z.y) * h.y + z.y * v[4 * q + 1];
+        v[4 * q + 2] = (1.f - z.z) * h.z + z.z * v[4 * q + 2];
+        v[4 * q + 3] = (1.f - z.w) * h.w + z.w * v[4 * q + 3];
+      }
     }
     if (e.out_f32) {
       float4* op = reinterpret_cast<float4*>(e.out_f32 + o);
@@ -164,6 +186,11 @@ __device__ __forceinline__ void epi_chunk(const EpiArgs& e, const uint32_t (&raw
         float x = v[j];
         if (e.aux_mode == FGT_AUX_ADD) x += __ldg(e.aux + o);
         else if (e.aux_mode == FGT_AUX_MUL) x *= __ldg(e.aux + o);
+        else if (e.aux_mode == FGT_AUX_ADD_RELU) x = fmaxf(x + __ldg(e.aux + o), 0.f);
+        else if (e.aux_mode == FGT_AUX_GRU) {
+          const float z = __ldg(e.aux2 + o);
+          x = (1.f - z) * __ldg(e.aux + o) + z * x;
+        }
         if (e.out_f32) e.out_f32[o] = x;
         if (e.out_hi) {
           __nv_bfloat16 h, l;
@@ -299,7 +326,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     const int quarter = warp & 3;  // TMEM lane quarter this warp may read
     const int r = quarter * 32 + lane;
     EpiArgs ep;
-    ep.out_f32 = p.out_f32; ep.out_hi = p.out_hi; ep.aux = p.aux; ep.out_plane = p.out_plane; ep.os_c = p.os_c;
+    ep.out_f32 = p.out_f32; ep.out_hi = p.out_hi; ep.aux = p.aux; ep.aux2 = p.aux2; ep.out_plane = p.out_plane; ep.os_c = p.os_c;
     ep.alpha = p.alpha; ep.act = p.act; ep.aux_mode = p.aux_mode; ep.vec_ok = p.vec_ok; ep.N = p.N;
     const int e_bn = p.bn, e_bn_p2 = p.bn_p2, e_N = p.N;
     int lt = 0;
@@ -403,6 +430,7 @@ int gemm_tc_launch(const FgtGemmDesc& d, cudaStream_t stream) {
               FGT_ERR_ARG, "gemm_tc: box %dx%d", d.box_w, d.box_h);
   FGT_REQUIRE(d.out_f32 || d.out_hi, FGT_ERR_ARG, "gemm_tc: no output");
   FGT_REQUIRE(d.aux_mode == FGT_AUX_NONE || d.aux, FGT_ERR_ARG, "gemm_tc: aux_mode without aux");
+  FGT_REQUIRE(d.aux_mode != FGT_AUX_GRU || d.aux2, FGT_ERR_ARG, "gemm_tc: FGT_AUX_GRU needs aux2");
   FGT_REQUIRE((reinterpret_cast<uintptr_t>(d.w_hi) & 15) == 0 && d.k_pad % 64 == 0, FGT_ERR_ARG,
               "gemm_tc: weights misaligned / k_pad=%d", d.k_pad);
 
@@ -495,6 +523,7 @@ int gemm_tc_launch(const FgtGemmDesc& d, cudaStream_t stream) {
   p.out_hi = reinterpret_cast<__nv_bfloat16*>(d.out_hi);
   p.out_plane = d.out_plane;
   p.aux = d.aux;
+  p.aux2 = d.aux2;
   p.aux_mode = d.aux_mode;
   p.bias = d.bias;
   p.act = d.act;
@@ -502,7 +531,7 @@ int gemm_tc_launch(const FgtGemmDesc& d, cudaStream_t stream) {
   // 16-byte vector path: unit channel stride and every address component a multiple of 8 elements
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.vec_ok = (d.os_c == 1 && d.os_x % 8 == 0 && d.os_y % 8 == 0 && d.os_z % 8 == 0 && d.out_plane % 8 == 0 &&
-              al(d.out_f32) && al(d.out_hi) && al(d.aux))
+              al(d.out_f32) && al(d.out_hi) && al(d.aux) && al(d.aux2))
                  ? 1
                  : 0;
 

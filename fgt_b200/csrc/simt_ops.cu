@@ -57,7 +57,8 @@ __global__ void pack_nchw_kernel(const float* __restrict__ s0, int c0, const flo
 // ------------------------------------------------------------------------------------------
 __global__ void im2col_nchw_kernel(const float* __restrict__ s0, int c0, const float* __restrict__ s1, int c1,
                                    int n, int H, int W, int k, int stride, int pad, int replicate, int OH, int OW,
-                                   int cpad, __nv_bfloat16* __restrict__ hi, long long plane) {
+                                   int cpad, float scale, float shift, __nv_bfloat16* __restrict__ hi,
+                                   long long plane) {
   const int cin = c0 + c1;
   const int groups = cpad / 8;
   const long long total = static_cast<long long>(n) * OH * OW * groups;
@@ -84,8 +85,9 @@ __global__ void im2col_nchw_kernel(const float* __restrict__ s0, int c0, const f
           ok = y >= 0 && y < H && x >= 0 && x < W;
         }
         if (ok)
-          val = (c < c0) ? __ldg(s0 + ((static_cast<long long>(b) * c0 + c) * H + y) * W + x)
-                         : __ldg(s1 + ((static_cast<long long>(b) * c1 + (c - c0)) * H + y) * W + x);
+          val = fmaf((c < c0) ? __ldg(s0 + ((static_cast<long long>(b) * c0 + c) * H + y) * W + x)
+                              : __ldg(s1 + ((static_cast<long long>(b) * c1 + (c - c0)) * H + y) * W + x),
+                     scale, shift);
       }
       v[j] = val;
     }
@@ -371,15 +373,15 @@ extern "C" int fgt_pack_nchw(const float* src0, int c0, const float* src1, int c
 }
 
 extern "C" int fgt_im2col_nchw(const float* src0, int c0, const float* src1, int c1, int n, int H, int W, int k,
-                               int stride, int pad, int replicate, int OH, int OW, int cpad, void* out_hi,
-                               long long out_plane, fgt_stream_t stream) {
+                               int stride, int pad, int replicate, int OH, int OW, int cpad, float scale, float shift,
+                               void* out_hi, long long out_plane, fgt_stream_t stream) {
   FGT_REQUIRE(src0 && c0 >= 1 && (c1 == 0 || src1) && cpad % 8 == 0 && k * k * (c0 + c1) <= cpad && k >= 1 &&
                   stride >= 1,
               FGT_ERR_ARG, "im2col_nchw: k=%d cin=%d cpad=%d", k, c0 + c1, cpad);
   const long long total = static_cast<long long>(n) * OH * OW * (cpad / 8);
   im2col_nchw_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      src0, c0, src1, c1, n, H, W, k, stride, pad, replicate, OH, OW, cpad, reinterpret_cast<__nv_bfloat16*>(out_hi),
-      out_plane);
+      src0, c0, src1, c1, n, H, W, k, stride, pad, replicate, OH, OW, cpad, scale, shift,
+      reinterpret_cast<__nv_bfloat16*>(out_hi), out_plane);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;
 }

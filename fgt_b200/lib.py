@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfgt_sm100a.so")
 
 ACT_NONE, ACT_LEAKY02, ACT_RELU, ACT_SIGMOID, ACT_TANH, ACT_LEAKY001 = 0, 1, 2, 3, 4, 5
-AUX_NONE, AUX_ADD, AUX_MUL, AUX_ADD_PRE = 0, 1, 2, 3
+AUX_NONE, AUX_ADD, AUX_MUL, AUX_ADD_PRE, AUX_ADD_RELU, AUX_GRU = 0, 1, 2, 3, 4, 5
 
 _c_ll = ctypes.c_longlong
 _c_p = ctypes.c_void_p
@@ -38,7 +38,7 @@ class FgtGemmDesc(ctypes.Structure):
                 ("aux", _c_p), ("aux_mode", ctypes.c_int),
                 ("out_f32", _c_p), ("out_hi", _c_p), ("out_plane", _c_ll),
                 ("os_z", _c_ll), ("os_y", _c_ll), ("os_x", _c_ll), ("os_c", _c_ll),
-                ("rowmap", _c_p), ("lin_batch", ctypes.c_int)]
+                ("rowmap", _c_p), ("lin_batch", ctypes.c_int), ("aux2", _c_p)]
 
 
 class FgtAttnDesc(ctypes.Structure):
@@ -73,7 +73,7 @@ def load():
     lib.fgt_attention.restype = ctypes.c_int
     ci, cf, cll = ctypes.c_int, ctypes.c_float, _c_ll
     lib.fgt_pack_nchw.argtypes = [_c_p, ci, _c_p, ci, ci, ci, ci, ci, ci, _c_p, cll, _c_p]
-    lib.fgt_im2col_nchw.argtypes = [_c_p, ci, _c_p, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, _c_p, cll, _c_p]
+    lib.fgt_im2col_nchw.argtypes = [_c_p, ci, _c_p, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, cf, cf, _c_p, cll, _c_p]
     lib.fgt_im2col_nchw.restype = ctypes.c_int
     lib.fgt_rownorm.argtypes = [_c_p, ci, ci, _c_p, ci, ci, _c_p, ci, cll, ci, ci, _c_p, _c_p, _c_p, cll, cf, _c_p]
     lib.fgt_dwpool.argtypes = [_c_p, ci, _c_p, ci, ci, ci, ci, ci, ci, ci, _c_p, _c_p, _c_p, _c_p]
@@ -83,6 +83,17 @@ def load():
     lib.fgt_upsample2x.argtypes = [_c_p, cll, ci, ci, ci, ci, _c_p, cll, _c_p]
     for fn in (lib.fgt_pack_nchw, lib.fgt_rownorm, lib.fgt_dwpool, lib.fgt_dwconv3x3_res, lib.fgt_fold,
                lib.fgt_unfold, lib.fgt_upsample2x):
+        fn.restype = ctypes.c_int
+    cd = ctypes.c_double
+    lib.fgt_chan_stats.argtypes = [_c_p, ci, ci, ci, _c_p, _c_p]
+    lib.fgt_instnorm_act.argtypes = [_c_p, _c_p, ci, ci, ci, cf, ci, _c_p, _c_p, _c_p, cll, _c_p]
+    lib.fgt_avgpool2.argtypes = [_c_p, cll, ci, ci, _c_p, _c_p]
+    lib.fgt_corr_lookup.argtypes = [ctypes.POINTER(_c_p), ctypes.POINTER(ci), ctypes.POINTER(ci), ci, ci, _c_p, ci,
+                                    ci, _c_p, cll, _c_p]
+    lib.fgt_raft_flow_update.argtypes = [_c_p, _c_p, ci, ci, _c_p, _c_p, cll, ci, ci, _c_p]
+    lib.fgt_convex_upsample.argtypes = [_c_p, _c_p, ci, ci, _c_p, _c_p]
+    for fn in (lib.fgt_chan_stats, lib.fgt_instnorm_act, lib.fgt_avgpool2, lib.fgt_corr_lookup,
+               lib.fgt_raft_flow_update, lib.fgt_convex_upsample):
         fn.restype = ctypes.c_int
     _lib = lib
     return lib
@@ -163,7 +174,8 @@ def empty_split(shape, device):
 
 
 def plane_elems(s):
-    return s[0].numel()
+    """Element offset from the hi plane to the lo plane (works for row-sliced views too)."""
+    return s.stride(0)
 
 
 class ASeg:
@@ -184,7 +196,7 @@ class ASeg:
 def gemm_tc(segs, w_split, N, *, kx=1, ky=1, kz=1, stride=1, dil=1, pad_x=0, pad_y=0, pad_z=0, groups=1,
             out_w, out_h=1, out_z=1, box_w=128, box_h=1, bn=128, bias=None, alpha=1.0, act=ACT_NONE,
             aux=None, aux_mode=AUX_NONE, out_f32=None, out_split=None, out_elem_offset=0,
-            os_z=0, os_y=0, os_x=None, os_c=1, rowmap=None, lin_batch=0, tag=""):
+            os_z=0, os_y=0, os_x=None, os_c=1, rowmap=None, lin_batch=0, aux2=None, tag=""):
     """Generic launcher for fgt_gemm_tc. Output strides are in elements; see include/fgt_b200.h."""
     lib = load()
     d = FgtGemmDesc()
@@ -212,6 +224,7 @@ def gemm_tc(segs, w_split, N, *, kx=1, ky=1, kz=1, stride=1, dil=1, pad_x=0, pad
     d.act = act
     d.aux = (aux.data_ptr() + 4 * out_elem_offset) if aux is not None else None
     d.aux_mode = aux_mode
+    d.aux2 = (aux2.data_ptr() + 4 * out_elem_offset) if aux2 is not None else None
     d.out_f32 = (out_f32.data_ptr() + 4 * out_elem_offset) if out_f32 is not None else None
     if out_split is not None:
         d.out_hi = out_split.data_ptr() + 2 * out_elem_offset
@@ -265,14 +278,15 @@ def pack_nchw(src0, src1, out_split, pad=0, tag=""):
                                    plane_elems(out_split), stream_ptr()), "fgt_pack_nchw")
 
 
-def im2col_nchw(src0, src1, out_split, *, k, stride, pad, replicate, OH, OW, tag=""):
+def im2col_nchw(src0, src1, out_split, *, k, stride, pad, replicate, OH, OW, scale=1.0, shift=0.0, tag=""):
     """[n,c0,H,W] (+[n,c1,H,W]) fp32 -> [2, n, OH, OW, cpad] split rows of k*k*cin gathered inputs."""
     n, c0, H, W = src0.shape
     c1 = src1.shape[1] if src1 is not None else 0
     cpad = out_split.shape[-1]
     with _Prof("im2col_nchw", tag, 0, 4.0 * n * (c0 + c1) * H * W + 4.0 * out_split[0].numel()):
         check(load().fgt_im2col_nchw(_dp(src0), c0, _dp(src1), c1, n, H, W, k, stride, pad, 1 if replicate else 0,
-                                     OH, OW, cpad, _dp(out_split), plane_elems(out_split), stream_ptr()),
+                                     OH, OW, cpad, scale, shift, _dp(out_split), plane_elems(out_split),
+                                     stream_ptr()),
               "fgt_im2col_nchw")
 
 
@@ -318,3 +332,47 @@ def upsample2x(in_split, n, H, W, C, out_split, tag=""):
     with _Prof("upsample2x", tag, 0, 4.0 * n * H * W * C * 5):
         check(load().fgt_upsample2x(_dp(in_split), plane_elems(in_split), n, H, W, C, _dp(out_split),
                                     plane_elems(out_split), stream_ptr()), "fgt_upsample2x")
+
+
+# ------------------------------------------------------------------------------------------ RAFT helpers
+def chan_stats(x, n, HW, C, stats, tag=""):
+    with _Prof("chan_stats", tag, 0, 4.0 * n * HW * C):
+        check(load().fgt_chan_stats(_dp(x), n, HW, C, _dp(stats), stream_ptr()), "fgt_chan_stats")
+
+
+def instnorm_act(x, stats, n, HW, C, *, relu=True, res=None, out=None, out_split=None, eps=1e-5, tag=""):
+    with _Prof("instnorm_act", tag, 0, 4.0 * n * HW * C * (3 if res is not None else 2)):
+        check(load().fgt_instnorm_act(_dp(x), _dp(stats), n, HW, C, eps, 1 if relu else 0, _dp(res), _dp(out),
+                                      _dp(out_split), plane_elems(out_split) if out_split is not None else 0,
+                                      stream_ptr()), "fgt_instnorm_act")
+
+
+def avgpool2(src, rows, h, w, dst, tag=""):
+    with _Prof("avgpool2", tag, 0, 5.0 * rows * h * w):
+        check(load().fgt_avgpool2(_dp(src), rows, h, w, _dp(dst), stream_ptr()), "fgt_avgpool2")
+
+
+def corr_lookup(levels, coords, n_pix, radius, out_split, tag=""):
+    """levels: list of fp32 tensors [n_pix, h_l, w_l]; out_split: [2, n_pix, pitch]."""
+    nl = len(levels)
+    ptrs = (_c_p * nl)(*[t.data_ptr() for t in levels])
+    hs = (ctypes.c_int * nl)(*[t.shape[1] for t in levels])
+    ws = (ctypes.c_int * nl)(*[t.shape[2] for t in levels])
+    win = 2 * radius + 1
+    with _Prof("corr_lookup", tag, 0, 4.0 * n_pix * nl * ((win + 1) ** 2 + win * win)):
+        check(load().fgt_corr_lookup(ptrs, hs, ws, nl, radius, _dp(coords), n_pix, out_split.shape[-1],
+                                     _dp(out_split), plane_elems(out_split), stream_ptr()), "fgt_corr_lookup")
+
+
+def raft_flow_update(coords, delta, h, w, flow_nchw, x_split=None, x_chan=0, tag=""):
+    with _Prof("raft_flow_update", tag, 0, 32.0 * h * w):
+        check(load().fgt_raft_flow_update(_dp(coords), _dp(delta), h, w, _dp(flow_nchw), _dp(x_split),
+                                          plane_elems(x_split) if x_split is not None else 0,
+                                          x_split.shape[-1] if x_split is not None else 0, x_chan, stream_ptr()),
+              "fgt_raft_flow_update")
+
+
+def convex_upsample(mask, flow_nchw, h, w, out, tag=""):
+    with _Prof("convex_upsample", tag, 0, 4.0 * h * w * (576 + 128)):
+        check(load().fgt_convex_upsample(_dp(mask), _dp(flow_nchw), h, w, _dp(out), stream_ptr()),
+              "fgt_convex_upsample")

@@ -39,7 +39,7 @@ def packed(name, weight, bias, dev, seg_counts=None, im2col_pad=None):
 
 def conv(xs, wp, *, kx=1, ky=1, kz=1, stride=1, dil=1, pad_x=0, pad_y=0, pad_z=0, out_z=None, act=lib.ACT_LEAKY02,
          out_split=None, out_f32=None, aux=None, aux_mode=lib.AUX_NONE, groups=1, seg_counts=None, nchw_out=False,
-         alpha=1.0):
+         alpha=1.0, aux2=None, out_c_total=None, out_c_offset=0):
     """xs: list of (split tensor [2, Z, Y, X, C], C) sharing Z/Y/X. Output NHWC [Z', Y', X', N]
     (or NCHW fp32 when nchw_out). Returns (oz, oy, ox)."""
     x0, c0 = xs[0]
@@ -56,10 +56,11 @@ def conv(xs, wp, *, kx=1, ky=1, kz=1, stride=1, dil=1, pad_x=0, pad_y=0, pad_z=0
     if nchw_out:
         strides = dict(os_z=N * oy * ox, os_y=ox, os_x=1, os_c=oy * ox)
     else:
-        strides = dict(os_z=oy * ox * N, os_y=ox * N, os_x=N, os_c=1)
+        ct = N if out_c_total is None else out_c_total  # write into a channel slice of a wider NHWC buffer
+        strides = dict(os_z=oy * ox * ct, os_y=ox * ct, os_x=ct, os_c=1, out_elem_offset=out_c_offset)
     lib.gemm_tc(segs, wp["w"], N, kx=kx, ky=ky, kz=kz, stride=stride, dil=dil, pad_x=pad_x, pad_y=pad_y, pad_z=pad_z,
                 groups=groups, out_w=ox, out_h=oy, out_z=oz, box_w=bw, box_h=bh, bn=pick_bn(N // groups, groups),
-                bias=wp["b"], alpha=alpha, act=act, aux=aux, aux_mode=aux_mode, out_f32=out_f32, out_split=out_split,
+                bias=wp["b"], alpha=alpha, act=act, aux=aux, aux_mode=aux_mode, aux2=aux2, out_f32=out_f32, out_split=out_split,
                 tag=wp["name"], **strides)
     return oz, oy, ox
 

@@ -223,3 +223,107 @@ def lafc_inputs(seed=0, T=3, H=240, W=432, b=1):
             masks[bi, 0, ti, y0:y0 + hh, x0:x0 + ww] = 1.0
     flows = flows.reshape(b, T, 2, H, W).permute(0, 2, 1, 3, 4).contiguous()
     return flows, masks
+
+
+# ----------------------------------------------------------------------------------------------
+# RAFT (basic model)
+# ----------------------------------------------------------------------------------------------
+def raft_param_shapes():
+    """state_dict contract of RAFT.RAFT (basic), /root/reference/RAFT/{raft,extractor,update}.py; same
+    179 keys as raft-things.pth minus the DataParallel 'module.' prefix."""
+    s = {}
+
+    def conv(name, co, ci, kh, kw=None):
+        s[name + ".weight"] = (co, ci, kh, kh if kw is None else kw)
+        s[name + ".bias"] = (co,)
+
+    def bn(name, c):
+        s[name + ".weight"] = (c,)
+        s[name + ".bias"] = (c,)
+        s[name + ".running_mean"] = (c,)
+        s[name + ".running_var"] = (c,)
+        s[name + ".num_batches_tracked"] = ()
+
+    def enc(pre, out_dim, batch_norm):
+        conv(pre + ".conv1", 64, 3, 7)
+        if batch_norm:
+            bn(pre + ".norm1", 64)
+        cin = 64
+        for li, (dim, stride) in enumerate(((64, 1), (96, 2), (128, 2)), start=1):
+            for bi in range(2):
+                k = f"{pre}.layer{li}.{bi}"
+                st = stride if bi == 0 else 1
+                conv(k + ".conv1", dim, cin if bi == 0 else dim, 3)
+                conv(k + ".conv2", dim, dim, 3)
+                if batch_norm:
+                    bn(k + ".norm1", dim)
+                    bn(k + ".norm2", dim)
+                if st != 1:
+                    conv(k + ".downsample.0", dim, cin, 1)
+                    if batch_norm:
+                        bn(k + ".norm3", dim)
+                        bn(k + ".downsample.1", dim)  # alias of norm3 in the reference module
+            cin = dim
+        conv(pre + ".conv2", out_dim, 128, 1)
+
+    enc("fnet", 256, False)
+    enc("cnet", 256, True)
+    u = "update_block."
+    conv(u + "encoder.convc1", 256, 324, 1)
+    conv(u + "encoder.convc2", 192, 256, 3)
+    conv(u + "encoder.convf1", 128, 2, 7)
+    conv(u + "encoder.convf2", 64, 128, 3)
+    conv(u + "encoder.conv", 126, 256, 3)
+    for g in "zrq":
+        conv(u + f"gru.conv{g}1", 128, 384, 1, 5)
+        conv(u + f"gru.conv{g}2", 128, 384, 5, 1)
+    conv(u + "flow_head.conv1", 256, 128, 3)
+    conv(u + "flow_head.conv2", 2, 256, 3)
+    conv(u + "mask.0", 256, 128, 3)
+    conv(u + "mask.2", 576, 256, 1)
+    return s
+
+
+def raft_state_dict(seed=0, flow_gain=0.5):
+    """Seeded RAFT weights: He-style conv weights (std = gain/sqrt(fan_in)), small random biases,
+    BatchNorm with random affine and running statistics; the flow head is damped (flow_gain) so the
+    20-step recurrence stays in a sane flow range with random weights."""
+    shapes = raft_param_shapes()
+    sd = {}
+    for key, shape in shapes.items():
+        g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(key.encode())) & 0x7FFFFFFF)
+        if key.endswith("num_batches_tracked"):
+            sd[key] = torch.tensor(100, dtype=torch.int64)
+        elif key.endswith("running_var"):
+            sd[key] = 0.5 + torch.rand(shape, generator=g)
+        elif key.endswith("running_mean"):
+            sd[key] = 0.1 * torch.randn(shape, generator=g)
+        elif len(shape) == 4:
+            fan_in = shape[1] * shape[2] * shape[3]
+            gain = 1.4
+            if "flow_head.conv2" in key:
+                gain = flow_gain
+            elif "gru.conv" in key or "mask.2" in key:
+                gain = 1.0
+            sd[key] = torch.randn(shape, generator=g) * (gain / math.sqrt(fan_in))
+        elif key.endswith(".weight"):  # BatchNorm gamma
+            sd[key] = 1.0 + 0.2 * torch.randn(shape, generator=g)
+        else:
+            sd[key] = 0.05 * torch.randn(shape, generator=g)
+    # the reference's downsample.1 IS norm3 (extractor.py:43-44): keep the aliases identical
+    for k in list(sd):
+        if ".downsample.1." in k:
+            sd[k] = sd[k.replace(".downsample.1.", ".norm3.")].clone()
+    return sd
+
+
+def raft_inputs(seed=0, H=480, W=864, n=1, shift=3.0):
+    """A smooth random image in [0,255] and a warped copy (global shift + smooth deformation)."""
+    g = torch.Generator().manual_seed(seed)
+    base = _smooth(torch.randn(n, 3, H + 32, W + 32, generator=g), k=9)
+    base = base + 0.3 * _smooth(torch.randn(n, 3, H + 32, W + 32, generator=g), k=3)
+    base = (base - base.amin()) / (base.amax() - base.amin()) * 255.0
+    dx, dy = int(shift), int(-shift // 2)
+    im1 = base[:, :, 16:16 + H, 16:16 + W].contiguous()
+    im2 = base[:, :, 16 + dy:16 + dy + H, 16 + dx:16 + dx + W].contiguous()
+    return im1, im2

@@ -44,8 +44,10 @@ enum {
 
 enum { FGT_ACT_NONE = 0, FGT_ACT_LEAKY02 = 1, FGT_ACT_RELU = 2, FGT_ACT_SIGMOID = 3, FGT_ACT_TANH = 4,
        FGT_ACT_LEAKY001 = 5 /* nn.LeakyReLU() default slope, LAFC/models/lafc.py:138 */ };
-/* aux: out = act(v) + aux | out = act(v) * aux | out = act(v + aux) */
-enum { FGT_AUX_NONE = 0, FGT_AUX_ADD = 1, FGT_AUX_MUL = 2, FGT_AUX_ADD_PRE = 3 };
+/* aux: out = act(v) + aux | act(v) * aux | act(v + aux) | relu(act(v) + aux) |
+ *      (1 - aux2) * aux + aux2 * act(v)   (the ConvGRU state update, RAFT/update.py:52,58) */
+enum { FGT_AUX_NONE = 0, FGT_AUX_ADD = 1, FGT_AUX_MUL = 2, FGT_AUX_ADD_PRE = 3, FGT_AUX_ADD_RELU = 4,
+       FGT_AUX_GRU = 5 };
 
 int fgt_version(void);
 const char* fgt_last_error(void);
@@ -100,6 +102,7 @@ typedef struct {
   long long os_z, os_y, os_x, os_c; /* output element strides for (z, y, x, channel) */
   const int* rowmap;         /* linear mode only (out_h == out_z == 1): row -> output row, <0 = drop */
   int lin_batch;             /* linear mode: if >0, z = row / lin_batch, x = row % lin_batch */
+  const float* aux2;         /* second fp32 operand (FGT_AUX_GRU: the update gate z), addressed like the output */
 } FgtGemmDesc;
 
 int fgt_gemm_tc(const FgtGemmDesc* desc, fgt_stream_t stream);
@@ -146,8 +149,8 @@ int fgt_pack_nchw(const float* src0, int c0, const float* src1, int c1, int n, i
  * nn.ReplicationPad2d(pad) followed by an unpadded conv). Feeds fgt_gemm_tc as a K=cpad linear layer.
  * Replaces the input side of nn.Conv2d at FGT/models/model.py:34 and model.py:207-208. */
 int fgt_im2col_nchw(const float* src0, int c0, const float* src1, int c1, int n, int H, int W, int k, int stride,
-                    int pad, int replicate, int OH, int OW, int cpad, void* out_hi, long long out_plane,
-                    fgt_stream_t stream);
+                    int pad, int replicate, int OH, int OW, int cpad, float scale, float shift, void* out_hi,
+                    long long out_plane, fgt_stream_t stream); /* in-bounds values become v*scale + shift */
 
 /* LayerNorm over the channel concatenation [a ; b] of fp32 rows. gamma/beta may be NULL (statistics
  * only: the affine is then folded into the consuming Linear at weight-pack time). Destination row of work item d is
@@ -182,6 +185,39 @@ int fgt_unfold(const float* img, int bt, int th, int tw, int C, int kh, int kw, 
 /* Nearest x2 upsampling of an NHWC split tensor (F.interpolate at network_blocks_2d.py:58-60). */
 int fgt_upsample2x(const void* in_hi, long long in_plane, int n, int H, int W, int C, void* out_hi,
                    long long out_plane, fgt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * RAFT helpers (HBM-bound). Tensors are NHWC fp32 unless noted.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Per-(image, channel) sum / sum-of-squares -> stats[n][C][2] (double). nn.InstanceNorm2d statistics,
+ * RAFT/extractor.py:29-33,131-132 (the normalisation itself is fgt_instnorm_act). */
+int fgt_chan_stats(const float* x, int n, int HW, int C, double* stats, fgt_stream_t stream);
+
+/* y = (x - mean) * rsqrt(var + eps) [ReLU] ; if res: y = relu(y + res). ResidualBlock.forward,
+ * RAFT/extractor.py:47-56 and BasicEncoder.forward :176-178 for the instance-norm feature net. */
+int fgt_instnorm_act(const float* x, const double* stats, int n, int HW, int C, float eps, int relu,
+                     const float* res, float* out, void* out_hi, long long out_plane, fgt_stream_t stream);
+
+/* 2x2 average pooling over the last two dims of [rows, h, w] (correlation pyramid, RAFT/corr.py:25-27). */
+int fgt_avgpool2(const float* in, long long rows, int h, int w, float* out, fgt_stream_t stream);
+
+/* CorrBlock.__call__ (RAFT/corr.py:29-50) + bilinear_sampler (RAFT/utils/utils.py:57-71): for each of
+ * n_pix source pixels and each pyramid level l (volume level_ptrs[l] = [n_pix, h_l, w_l] fp32), the
+ * (2r+1)^2 zero-padded bilinear samples around coords/2^l. Output split-bf16 [n_pix, out_pitch],
+ * channel = l*(2r+1)^2 + a*(2r+1) + b with a offsetting x and b offsetting y (reference order).
+ * level_ptrs_host / level_h_host / level_w_host are HOST arrays of `levels` entries. */
+int fgt_corr_lookup(const float* const* level_ptrs_host, const int* level_h_host, const int* level_w_host,
+                    int levels, int radius, const float* coords, int n_pix, int out_pitch, void* out_hi,
+                    long long out_plane, fgt_stream_t stream);
+
+/* coords += delta (delta may be NULL); writes flow = coords - pixel grid as NCHW fp32 [2,h,w] and, if
+ * x_hi != NULL, as channels [x_chan, x_chan+1] of the split GRU-input buffer (RAFT/raft.py:127-132). */
+int fgt_raft_flow_update(float* coords, const float* delta, int h, int w, float* flow_nchw, void* x_hi,
+                         long long x_plane, int x_pitch, int x_chan, fgt_stream_t stream);
+
+/* RAFT.upsample_flow (RAFT/raft.py:73-84): mask [h*w, 576] fp32 -> up-sampled flow [2, 8h, 8w]. */
+int fgt_convex_upsample(const float* mask, const float* flow_nchw, int h, int w, float* out, fgt_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -116,7 +116,54 @@ def lafc_case(name, H, W, regime, seed, sample=None):
     print(name, "flow std", flow.std().item(), "saved")
 
 
+def raft_case(name, H, W, iters, seed, sample=None):
+    import argparse
+    R = importlib.import_module("RAFT")
+    model = R.RAFT(argparse.Namespace(small=False, mixed_precision=False, alternate_corr=False)).eval()
+    sd = synth.raft_state_dict(seed=seed)
+    model.load_state_dict(sd)
+    im1, im2 = synth.raft_inputs(seed=seed + 1, H=H, W=W)
+    with torch.no_grad():
+        lo, up = model(im1, im2, iters=iters, test_mode=True)
+    meta = dict(H=H, W=W, iters=iters, seed=seed, **VERSIONS)
+    arrs = dict(meta=np.array(repr(meta)), lo_l2=np.float64(lo.double().norm().item()),
+                up_l2=np.float64(up.double().norm().item()))
+    if sample is None:
+        arrs["lo"] = lo.numpy().astype(np.float32)
+        arrs["up"] = up.numpy().astype(np.float32)
+    else:
+        g = torch.Generator().manual_seed(1234)
+        ui = torch.randperm(up.numel(), generator=g)[:sample]
+        arrs.update(lo=lo.numpy().astype(np.float32), up_idx=ui.numpy(), up_val=up.reshape(-1)[ui].numpy())
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrs)
+    print(name, "|flow|max", lo.abs().max().item(), "saved")
+
+
+def raft_real_weights_check():
+    """Pins the RAFT oracle with the REAL raft-things.pth (cannot travel to the GPU box, so assert-only)."""
+    import argparse
+    from oracle import raft_oracle as RO
+    R = importlib.import_module("RAFT")
+    model = R.RAFT(argparse.Namespace(small=False, mixed_precision=False, alternate_corr=False)).eval()
+    sd = torch.load(os.path.join(REF, "LAFC/flowCheckPoint/raft-things.pth"), map_location="cpu")
+    sd = {k[len("module."):]: v for k, v in sd.items()}
+    model.load_state_dict(sd)
+    im1, im2 = synth.raft_inputs(seed=1, H=128, W=192)
+    with torch.no_grad():
+        lo, up = model(im1, im2, iters=20, test_mode=True)
+        olo, oup = RO.raft_forward(sd, im1, im2, iters=20)
+    err = ((oup - up).norm() / up.norm()).item()
+    assert err < 1e-6, err
+    print("raft oracle vs reference with raft-things.pth: rel", err, "mean flow", up.mean(dim=(0, 2, 3)).tolist())
+
+
 if __name__ == "__main__":
+    if "--raft-only" in sys.argv:
+        raft_real_weights_check()
+        raft_case("raft_small_i6", 128, 192, 6, seed=3)
+        raft_case("raft_small_i20", 128, 192, 20, seed=3)
+        raft_case("raft_full_i20", 480, 864, 20, seed=4, sample=8192)
+        sys.exit(0)
     lafc_case("lafc_small_scaled", 64, 96, "scaled", seed=4)
     lafc_case("lafc_small_kaiming", 64, 96, "kaiming", seed=4)
     lafc_case("lafc_full", 240, 432, "scaled", seed=5, sample=8192)
