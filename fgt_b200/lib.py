@@ -95,6 +95,12 @@ def load():
     for fn in (lib.fgt_chan_stats, lib.fgt_instnorm_act, lib.fgt_avgpool2, lib.fgt_corr_lookup,
                lib.fgt_raft_flow_update, lib.fgt_convex_upsample):
         fn.restype = ctypes.c_int
+    lib.fgt_prop_step.argtypes = [_c_p, _c_p, _c_p, ci, ci, ci, ci, cd, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p]
+    lib.fgt_prop_gather.argtypes = [_c_p, _c_p, _c_p, _c_p, ci, ci, ci, ci, _c_p, _c_p, _c_p]
+    lib.fgt_prop_fuse.argtypes = [_c_p, _c_p, _c_p, _c_p, _c_p, ci, ci, ci, cd, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p,
+                                  _c_p, _c_p]
+    for fn in (lib.fgt_prop_step, lib.fgt_prop_gather, lib.fgt_prop_fuse):
+        fn.restype = ctypes.c_int
     _lib = lib
     return lib
 

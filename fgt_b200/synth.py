@@ -327,3 +327,29 @@ def raft_inputs(seed=0, H=480, W=864, n=1, shift=3.0):
     im1 = base[:, :, 16:16 + H, 16:16 + W].contiguous()
     im2 = base[:, :, 16 + dy:16 + dy + H, 16 + dx:16 + dx + W].contiguous()
     return im1, im2
+
+
+# ----------------------------------------------------------------------------------------------
+# flow-guided gradient propagation (get_flowNN_gradient)
+# ----------------------------------------------------------------------------------------------
+def prop_inputs(seed=0, H=64, W=96, N=6):
+    """numpy inputs shaped like the driver's call (tool/video_inpainting.py:585-633): gradients
+    [H,W,3,N] float32 (zero under the dilated mask), mask [H,W,N] bool (a moving box + a static blob),
+    forward / backward flows [H,W,2,N-1] float32 that are approximately mutually consistent."""
+    import numpy as np
+    g = torch.Generator().manual_seed(seed)
+    fl = _smooth(torch.randn(N - 1, 2, H, W, generator=g), k=11) * 25.0 + torch.tensor([1.5, -0.8]).view(1, 2, 1, 1)
+    noise = _smooth(torch.randn(N - 1, 2, H, W, generator=g), k=5) * 1.5
+    flow_f = fl.permute(2, 3, 1, 0).contiguous().numpy().astype(np.float32)
+    flow_b = (-fl + noise).permute(2, 3, 1, 0).contiguous().numpy().astype(np.float32)
+    mask = np.zeros((H, W, N), dtype=bool)
+    for t in range(N):
+        y0, x0 = H // 4 + t, W // 5 + 2 * t
+        mask[y0:y0 + H // 3, x0:x0 + W // 3, t] = True
+        mask[H - 14:H - 4, W - 20:W - 6, t] = True
+    gx = torch.randn(H, W, 3, N, generator=g).numpy().astype(np.float32)
+    gy = torch.randn(H, W, 3, N, generator=g).numpy().astype(np.float32)
+    for t in range(N):
+        gx[mask[:, :, t], :, t] = 0
+        gy[mask[:, :, t], :, t] = 0
+    return gx, gy, mask, flow_f, flow_b

@@ -219,6 +219,30 @@ int fgt_raft_flow_update(float* coords, const float* delta, int h, int w, float*
 /* RAFT.upsample_flow (RAFT/raft.py:73-84): mask [h*w, 576] fp32 -> up-sampled flow [2, 8h, 8w]. */
 int fgt_convex_upsample(const float* mask, const float* flow_nchw, int h, int w, float* out, fgt_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Flow-guided gradient propagation (tool/get_flowNN_gradient.py:11-534, Nonlocal=False). Dense state
+ * per NN slot (0 = backward-flow neighbours, 1 = forward-flow neighbours), all [N,H,W]:
+ *   nn_y, nn_x (double), nn_t (int, -1 = none), have (uint8: 1 = neighbour found), cuv (double[2]).
+ * mask is uint8 [N,H,W]; flows are float [H,W,2] = (u, v) of one frame pair; gradients float [N,H,W,3].
+ * ------------------------------------------------------------------------------------------ */
+
+/* One frame `t` of one pass (neighbour frame tn = t-1 for slot 0, t+1 for slot 1); `flow_step` moves
+ * t -> tn, `flow_back` tn -> t. Replaces the loop bodies at get_flowNN_gradient.py:76-235 / 241-370 and
+ * BFconsistCheck / FBconsistCheck / consistCheck (tool/utils/common_utils.py:187-254). */
+int fgt_prop_step(const uint8_t* mask, const float* flow_step, const float* flow_back, int H, int W, int t, int tn,
+                  double thres, double* nn_y, double* nn_x, int* nn_t, uint8_t* have, double* cuv,
+                  fgt_stream_t stream);
+
+/* In-place gather for source frame s (get_flowNN_gradient.py:378-435 + interp, common_utils.py:149-171):
+ * cv2.remap-compatible bilinear sampling (1/32-pixel fixed-point coordinates, zero border). */
+int fgt_prop_gather(const uint8_t* mask, const double* nn_y, const double* nn_x, const int* nn_t, int N, int H, int W,
+                    int s, float* gx, float* gy, fgt_stream_t stream);
+
+/* Confidence-weighted fusion of the two candidates and the still-to-fill mask (get_flowNN_gradient.py:440-532). */
+int fgt_prop_fuse(const uint8_t* mask, const uint8_t* have0, const uint8_t* have1, const double* cuv0,
+                  const double* cuv1, int N, int H, int W, double alpha, const float* gx_bn, const float* gy_bn,
+                  const float* gx_fn, const float* gy_fn, float* gx, float* gy, uint8_t* tofill, fgt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

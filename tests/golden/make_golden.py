@@ -157,7 +157,31 @@ def raft_real_weights_check():
     print("raft oracle vs reference with raft-things.pth: rel", err, "mean flow", up.mean(dim=(0, 2, 3)).tolist())
 
 
+def prop_case(name, H, W, N, thres, seed):
+    import argparse
+    import contextlib
+    import io
+    sys.path.insert(0, os.path.join(REF, "tool"))
+    from get_flowNN_gradient import get_flowNN_gradient
+    gx, gy, mask, ff, fb = synth.prop_inputs(seed=seed, H=H, W=W, N=N)
+    args = argparse.Namespace(Nonlocal=False, consistencyThres=thres, alpha=0.1)
+    with contextlib.redirect_stdout(io.StringIO()):
+        rx, ry, rm = get_flowNN_gradient(args, gx.copy(), gy.copy(), mask.copy(), mask.copy(), ff, fb, None, None)
+    import cv2
+    meta = dict(H=H, W=W, N=N, thres=thres, seed=seed, cv2=cv2.__version__, **VERSIONS)
+    hole = np.repeat(mask[:, :, None, :], 3, axis=2)
+    assert np.array_equal(rx[~hole], gx[~hole]) and np.array_equal(ry[~hole], gy[~hole])  # only holes change
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=np.array(repr(meta)), gx_hole=rx[hole],
+                        gy_hole=ry[hole], tofill=np.packbits(rm))
+    print(name, "holes", int(mask.sum()), "tofill", int(rm.sum()), "saved")
+
+
 if __name__ == "__main__":
+    if "--prop-only" in sys.argv:
+        prop_case("prop_small", 64, 96, 6, 5.0, seed=2)
+        prop_case("prop_thres1", 48, 64, 4, 1.0, seed=3)
+        prop_case("prop_mid", 120, 160, 8, 5.0, seed=4)
+        sys.exit(0)
     if "--raft-only" in sys.argv:
         raft_real_weights_check()
         raft_case("raft_small_i6", 128, 192, 6, seed=3)
