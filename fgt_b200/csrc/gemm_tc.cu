@@ -76,7 +76,9 @@ struct EpiArgs {
   int act, aux_mode, vec_ok, N;
 };
 
-template <int NC>
+// kExt = 1 adds the rarely used epilogue modes (pre-activation add, add+ReLU, GRU update, slope-0.01
+// LeakyReLU); keeping them out of the common instantiation keeps it at ~150 registers with no spills.
+template <int NC, int kExt>
 __device__ __forceinline__ void epi_chunk(const EpiArgs& e, const uint32_t (&raw)[NC], const float* sb, long long off,
                                           int col0) {
   float v[NC];
@@ -89,7 +91,7 @@ __device__ __forceinline__ void epi_chunk(const EpiArgs& e, const uint32_t (&raw
     v[4 * q + 3] = fmaf(__uint_as_float(raw[4 * q + 3]), e.alpha, b.w);
   }
   const bool vec = e.vec_ok && col0 + NC <= e.N;
-  if (e.aux_mode == FGT_AUX_ADD_PRE) {  // residual added BEFORE the activation (LAFC edge head)
+  if (kExt && e.aux_mode == FGT_AUX_ADD_PRE) {  // residual added BEFORE the activation (LAFC edge head)
     if (vec) {
       const float4* ap = reinterpret_cast<const float4*>(e.aux + off + col0);
 #pragma unroll
@@ -105,7 +107,7 @@ __device__ __forceinline__ void epi_chunk(const EpiArgs& e, const uint32_t (&raw
   if (e.act == FGT_ACT_LEAKY02) {
 #pragma unroll
     for (int j = 0; j < NC; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
-  } else if (e.act == FGT_ACT_LEAKY001) {
+  } else if (kExt && e.act == FGT_ACT_LEAKY001) {
 #pragma unroll
     for (int j = 0; j < NC; ++j) v[j] = v[j] > 0.f ? v[j] : 0.01f * v[j];
   } else if (e.act == FGT_ACT_RELU) {
@@ -134,7 +136,7 @@ __device__ __forceinline__ void epi_chunk(const EpiArgs& e, const uint32_t (&raw
         const float4 a = __ldg(ap + q);
         v[4 * q] *= a.x; v[4 * q + 1] *= a.y; v[4 * q + 2] *= a.z; v[4 * q + 3] *= a.w;
       }
-    } else if (e.aux_mode == FGT_AUX_ADD_RELU) {
+    } else if (kExt && e.aux_mode == FGT_AUX_ADD_RELU) {
       const float4* ap = reinterpret_cast<const float4*>(e.aux + o);
 #pragma unroll
       for (int q = 0; q < NC / 4; ++q) {
@@ -142,7 +144,7 @@ __device__ __forceinline__ void epi_chunk(const EpiArgs& e, const uint32_t (&raw
         v[4 * q] = fmaxf(v[4 * q] + a.x, 0.f); v[4 * q + 1] = fmaxf(v[4 * q + 1] + a.y, 0.f);
         v[4 * q + 2] = fmaxf(v[4 * q + 2] + a.z, 0.f); v[4 * q + 3] = fmaxf(v[4 * q + 3] + a.w, 0.f);
       }
-    } else if (e.aux_mode == FGT_AUX_GRU) {  // h' = (1 - z) * h + z * q   (aux = h, aux2 = z, v = q)
+    } else if (kExt && e.aux_mode == FGT_AUX_GRU) {  // h' = (1 - z) * h + z * q   (aux = h, aux2 = z, v = q)
       const float4* hp4 = reinterpret_cast<const float4*>(e.aux + o);
       const float4* zp4 = reinterpret_cast<const float4*>(e.aux2 + o);
 #pragma unroll
@@ -167,13 +169,7 @@ __device__ __forceinline__ void epi_chunk(const EpiArgs& e, const uint32_t (&raw
       for (int q = 0; q < NC / 8; ++q) {
         uint32_t hw[4], lw[4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(v[8 * q + 2 * t], h0, l0);
-          split_bf16(v[8 * q + 2 * t + 1], h1, l1);
-          hw[t] = pack_bf16x2(h0, h1);
-          lw[t] = pack_bf16x2(l0, l1);
-        }
+        for (int t = 0; t < 4; ++t) split_bf16x2(v[8 * q + 2 * t], v[8 * q + 2 * t + 1], hw[t], lw[t]);
         hp[q] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
         lp[q] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
       }
@@ -186,8 +182,8 @@ __device__ __forceinline__ void epi_chunk(const EpiArgs& e, const uint32_t (&raw
         float x = v[j];
         if (e.aux_mode == FGT_AUX_ADD) x += __ldg(e.aux + o);
         else if (e.aux_mode == FGT_AUX_MUL) x *= __ldg(e.aux + o);
-        else if (e.aux_mode == FGT_AUX_ADD_RELU) x = fmaxf(x + __ldg(e.aux + o), 0.f);
-        else if (e.aux_mode == FGT_AUX_GRU) {
+        else if (kExt && e.aux_mode == FGT_AUX_ADD_RELU) x = fmaxf(x + __ldg(e.aux + o), 0.f);
+        else if (kExt && e.aux_mode == FGT_AUX_GRU) {
           const float z = __ldg(e.aux2 + o);
           x = (1.f - z) * __ldg(e.aux + o) + z * x;
         }
@@ -203,6 +199,7 @@ __device__ __forceinline__ void epi_chunk(const EpiArgs& e, const uint32_t (&raw
   }
 }
 
+template <int kExt>
 __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms.
@@ -382,14 +379,14 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
           uint32_t raw[32];
           tmem_ld32(t_row + c0, raw);
           tmem_ld_wait();
-          if (valid && n0 + c0 < e_N) epi_chunk<32>(ep, raw, sbias + c0, off, n0 + c0);
+          if (valid && n0 + c0 < e_N) epi_chunk<32, kExt>(ep, raw, sbias + c0, off, n0 + c0);
         }
       } else {
         for (int c0 = 0; c0 < e_bn; c0 += 16) {
           uint32_t raw[16];
           tmem_ld16(t_row + c0, raw);
           tmem_ld_wait();
-          if (valid && n0 + c0 < e_N) epi_chunk<16>(ep, raw, sbias + c0, off, n0 + c0);
+          if (valid && n0 + c0 < e_N) epi_chunk<16, kExt>(ep, raw, sbias + c0, off, n0 + c0);
         }
       }
       tc_fence_before();
@@ -544,13 +541,17 @@ int gemm_tc_launch(const FgtGemmDesc& d, cudaStream_t stream) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    FGT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FGT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FGT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
+  const bool ext = d.aux_mode == FGT_AUX_ADD_PRE || d.aux_mode == FGT_AUX_ADD_RELU || d.aux_mode == FGT_AUX_GRU ||
+                   d.act == FGT_ACT_LEAKY001;
   int grid = num_sms();
   if (grid > p.total_tiles) grid = p.total_tiles;
   FGT_REQUIRE(grid >= 1, FGT_ERR_ARG, "gemm_tc: empty problem");
-  gemm_tc_kernel<<<grid, 192, smem, stream>>>(p);
+  if (ext) gemm_tc_kernel<1><<<grid, 192, smem, stream>>>(p);
+  else gemm_tc_kernel<0><<<grid, 192, smem, stream>>>(p);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;
 }

@@ -133,6 +133,10 @@ typedef struct {
 
 int fgt_attention(const FgtAttnDesc* desc, fgt_stream_t stream);
 
+/* Debug aid (not on the data path): with a device buffer of 3*64*8 int64, subsequent fgt_attention
+ * launches record clock64() of CTA (0,0,0) per role (TMA / MMA / softmax) and key tile; NULL disables. */
+int fgt_debug_flash_trace(long long* device_buf);
+
 /* ------------------------------------------------------------------------------------------
  * HBM-bound helpers (coalesced / vectorised CUDA-core kernels). "split" outputs are split-bf16.
  * ------------------------------------------------------------------------------------------ */
