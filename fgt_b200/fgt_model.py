@@ -10,6 +10,7 @@ them. All arithmetic runs in libfgt_sm100a.so (tcgen05 implicit-GEMM engine, fus
 attention, HBM-bound helpers) through fgt_b200.lib. There is no CPU / PyTorch fallback.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -136,7 +137,14 @@ def _pick_box(ow, oh):
     return best[1], best[2]
 
 
-def _pick_bn(n_per_group, groups):
+# Layers whose output-channel tile is 256 instead of 128 (measured: only the 640->512 grouped encoder
+# conv gains, 0.443 -> 0.403 ms; smaller problems lose to wave quantisation). Tuning knob for experiments.
+_BN256 = os.environ.get("FGT_BN256", "enc10").split(",")
+
+
+def _pick_bn(n_per_group, groups, name=""):
+    if n_per_group % 256 == 0 and name in _BN256:
+        return 256
     if n_per_group % 128 == 0:
         return 128
     if n_per_group <= 128:
@@ -294,9 +302,21 @@ class FGT(nn.Module):
             sblock(f"transformer.{i}.s_transformer.", f"s{i + 1}")
         perm_v2p = self._perm_hidden(self.cnum * 2).to(perm_ffn.device)
         put("vec2patch", sd["vec2patch.embedding.weight"][perm_v2p], sd["vec2patch.embedding.bias"][perm_v2p])
-        conv("dec1", "decoder.layer1.conv.featureConv")
+        # VanillaDeconv = nearest x2 then 3x3 conv (network_blocks_2d.py:58-60). Output pixel (2i+py, 2j+px)
+        # only sees 2x2 low-res inputs, so each deconv becomes four 2x2 "phase" convs on the low-res map with
+        # pre-summed taps (2.25x fewer MACs, no upsampled intermediate): rows {i-1,i} for py=0, {i,i+1} for py=1.
+        def deconv(name, key):
+            w, b = sd[key + ".weight"], sd[key + ".bias"]
+            rows = {0: ([0], [1, 2]), 1: ([0, 1], [2])}  # phase -> 3x3 tap indices merged into each of the 2 taps
+            for py in (0, 1):
+                for px in (0, 1):
+                    w2 = torch.stack([torch.stack([w[:, :, rows[py][a], :][:, :, :, rows[px][c]].sum((2, 3))
+                                                   for c in (0, 1)], -1) for a in (0, 1)], -2)  # [co, ci, 2, 2]
+                    put(f"{name}.p{py}{px}", w2, b)
+
+        deconv("dec1", "decoder.layer1.conv.featureConv")
         conv("dec2", "decoder.layer2.featureConv")
-        conv("dec3", "decoder.layer3.conv.featureConv")
+        deconv("dec3", "decoder.layer3.conv.featureConv")
         conv("dec4", "decoder.final.featureConv")
         self._packed = P
         return P
@@ -383,13 +403,26 @@ class FGT(nn.Module):
         else:
             strides = dict(os_z=oh * ow * N, os_y=ow * N, os_x=N, os_c=1)
         lib.gemm_tc(segs, wp["w"], N, kx=k, ky=k, stride=stride, pad_x=pad, pad_y=pad, groups=groups, out_w=ow,
-                    out_h=oh, out_z=n, box_w=bw, box_h=bh, bn=_pick_bn(N // groups, groups), bias=wp["b"], act=act,
+                    out_h=oh, out_z=n, box_w=bw, box_h=bh, bn=_pick_bn(N // groups, groups, wp["name"]), bias=wp["b"], act=act,
                     out_f32=out_f32, out_split=out_split, tag=wp["name"], **strides)
         return oh, ow
 
     @staticmethod
+    def _deconv(x, cin, n, h, w, P, name, out_split):
+        """nearest-x2 + 3x3 conv + LeakyReLU as four 2x2 phase convs writing the interleaved [n,2h,2w,N] output."""
+        bw, bh = _pick_box(w, h)
+        for py in (0, 1):
+            for px in (0, 1):
+                wp = P[f"{name}.p{py}{px}"]
+                N = wp["N"]
+                lib.gemm_tc([lib.ASeg(x, cin, w, h, n)], wp["w"], N, kx=2, ky=2, pad_x=1 - px, pad_y=1 - py, out_w=w,
+                            out_h=h, out_z=n, box_w=bw, box_h=bh, bn=_pick_bn(N, 1, name), bias=wp["b"],
+                            act=lib.ACT_LEAKY02, out_split=out_split, out_elem_offset=(py * 2 * w + px) * N,
+                            os_z=4 * h * w * N, os_y=4 * w * N, os_x=2 * N, os_c=1, tag=wp["name"])
+
+    @staticmethod
     def _linear(segs, wp, rows, **kw):
-        lib.gemm_tc(segs, wp["w"], wp["N"], out_w=rows, bn=_pick_bn(wp["N"], 1), bias=wp["b"], tag=wp["name"], **kw)
+        lib.gemm_tc(segs, wp["w"], wp["N"], out_w=rows, bn=_pick_bn(wp["N"], 1, wp["name"]), bias=wp["b"], tag=wp["name"], **kw)
 
     def _ffn(self, g, P, name, x, xs, dev):
         """x += FusionFeedForward(LN(x)) (ffn_base.py:53-77, model.py:128-129 / 147-148)."""
@@ -550,17 +583,13 @@ class FGT(nn.Module):
         lib.fold(v2p, bt, g.h, g.w, self.cnum * 2, k, k, s, p, OH, OW, normalize=False, add=enc_f, out_split=feat)
         # ---- decoder (model.py:188-193,281-282)
         c2 = self.cnum * 2
-        up1 = B("up1", (bt, H2, W2, c2), split=True)
         d1 = B("d1", (bt, H2, W2, c2), split=True)
         d2 = B("d2", (bt, H2, W2, c2 // 2), split=True)
-        up2 = B("up2", (bt, H, W, c2 // 2), split=True)
         d3 = B("d3", (bt, H, W, c2 // 2), split=True)
         out = torch.empty(bt, 3, H, W, device=dev, dtype=torch.float32)
-        lib.upsample2x(feat, bt, OH, OW, c2, up1)
-        self._conv(up1, c2, bt, H2, W2, P["dec1"], 3, out_split=d1)
+        self._deconv(feat, c2, bt, OH, OW, P, "dec1", d1)
         self._conv(d1, c2, bt, H2, W2, P["dec2"], 3, out_split=d2)
-        lib.upsample2x(d2, bt, H2, W2, c2 // 2, up2)
-        self._conv(up2, c2 // 2, bt, H, W, P["dec3"], 3, out_split=d3)
+        self._deconv(d2, c2 // 2, bt, H2, W2, P, "dec3", d3)
         self._conv(d3, c2 // 2, bt, H, W, P["dec4"], 3, act=lib.ACT_TANH, out_f32=out, nchw_out=True)
         return out
 
