@@ -59,24 +59,36 @@ __global__ void im2col_nchw_kernel(const float* __restrict__ s0, int c0, const f
                                    int n, int H, int W, int k, int stride, int pad, int replicate, int OH, int OW,
                                    int cpad, float scale, float shift, __nv_bfloat16* __restrict__ hi,
                                    long long plane) {
+  // one block = one output row (b, oy); threadIdx.x = 8-channel group, threadIdx.y strides over ox.
+  // The channel -> (source channel, dy, dx) decode is a per-block shared-memory table: no per-element
+  // integer divisions in the loop (they dominated the first version of this kernel).
+  __shared__ short tab_c[256], tab_dy[256], tab_dx[256];
   const int cin = c0 + c1;
-  const int groups = cpad / 8;
-  const long long total = static_cast<long long>(n) * OH * OW * groups;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int g = static_cast<int>(i % groups);
-    const long long pix = i / groups;
-    const int ox = static_cast<int>(pix % OW);
-    const int oy = static_cast<int>((pix / OW) % OH);
-    const int b = static_cast<int>(pix / (static_cast<long long>(OW) * OH));
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  for (int ch = tid; ch < cpad; ch += blockDim.x * blockDim.y) {
+    if (ch < k * k * cin) {
+      const int tap = ch / cin;
+      tab_c[ch] = static_cast<short>(ch - tap * cin);
+      tab_dy[ch] = static_cast<short>(tap / k - pad);
+      tab_dx[ch] = static_cast<short>(tap % k - pad);
+    } else {
+      tab_c[ch] = -1;
+      tab_dy[ch] = tab_dx[ch] = 0;
+    }
+  }
+  __syncthreads();
+  const int b = blockIdx.x / OH, oy = blockIdx.x - b * OH;
+  const int g = threadIdx.x;
+  const long long HWl = static_cast<long long>(H) * W;
+  for (int ox = threadIdx.y; ox < OW; ox += blockDim.y) {
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int ch = g * 8 + j;
+      const int c = tab_c[ch];
       float val = 0.f;
-      if (ch < k * k * cin) {
-        const int tap = ch / cin, c = ch - tap * cin;
-        int y = oy * stride + tap / k - pad, x = ox * stride + tap % k - pad;
+      if (c >= 0) {
+        int y = oy * stride + tab_dy[ch], x = ox * stride + tab_dx[ch];
         bool ok = true;
         if (replicate) {
           y = min(max(y, 0), H - 1);
@@ -85,22 +97,16 @@ __global__ void im2col_nchw_kernel(const float* __restrict__ s0, int c0, const f
           ok = y >= 0 && y < H && x >= 0 && x < W;
         }
         if (ok)
-          val = fmaf((c < c0) ? __ldg(s0 + ((static_cast<long long>(b) * c0 + c) * H + y) * W + x)
-                              : __ldg(s1 + ((static_cast<long long>(b) * c1 + (c - c0)) * H + y) * W + x),
+          val = fmaf((c < c0) ? __ldg(s0 + (static_cast<long long>(b) * c0 + c) * HWl + y * W + x)
+                              : __ldg(s1 + (static_cast<long long>(b) * c1 + (c - c0)) * HWl + y * W + x),
                      scale, shift);
       }
       v[j] = val;
     }
     uint32_t hw[4], lw[4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      __nv_bfloat16 h0, l0, h1, l1;
-      split_bf16(v[2 * t], h0, l0);
-      split_bf16(v[2 * t + 1], h1, l1);
-      hw[t] = pack_bf16x2(h0, h1);
-      lw[t] = pack_bf16x2(l0, l1);
-    }
-    const long long o = pix * cpad + g * 8;
+    for (int t = 0; t < 4; ++t) split_bf16x2(v[2 * t], v[2 * t + 1], hw[t], lw[t]);
+    const long long o = ((static_cast<long long>(b) * OH + oy) * OW + ox) * cpad + g * 8;
     *reinterpret_cast<uint4*>(hi + o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
     *reinterpret_cast<uint4*>(hi + plane + o) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
   }
@@ -259,20 +265,17 @@ __global__ void dwconv3_res_kernel(const float* __restrict__ x, int bt, int h, i
 __global__ void fold_kernel(const float* __restrict__ hid, int bt, int th, int tw, int C, int kh, int kw, int st,
                             int pd, int OH, int OW, int normalize, const float* __restrict__ add,
                             float* __restrict__ out, __nv_bfloat16* __restrict__ hi, long long plane) {
+  // one block = one output row (b, y); threadIdx.x = float4 channel group, threadIdx.y strides over x.
+  // The contributing token rows are block-uniform; no per-element integer divisions by runtime values.
   const int C4 = C / 4;
-  const long long total = static_cast<long long>(bt) * OH * OW * C4;
   const int hidden = kh * kw * C;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % C4) * 4;
-    const long long pix = i / C4;
-    const int x = static_cast<int>(pix % OW);
-    const int y = static_cast<int>((pix / OW) % OH);
-    const long long f = pix / (static_cast<long long>(OW) * OH);
+  const int b = blockIdx.x / OH, y = blockIdx.x - b * OH;
+  const int c = threadIdx.x * 4;
+  if (threadIdx.x >= C4) return;
+  const int ty_hi = min((y + pd) / st, th - 1);
+  for (int x = threadIdx.y; x < OW; x += blockDim.y) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int cnt = 0;
-    // tokens ty with 0 <= y + pd - st*ty < kh
-    const int ty_hi = min((y + pd) / st, th - 1);
     const int tx_hi = min((x + pd) / st, tw - 1);
     for (int ty = ty_hi; ty >= 0; --ty) {
       const int ky = y + pd - st * ty;
@@ -281,19 +284,19 @@ __global__ void fold_kernel(const float* __restrict__ hid, int bt, int th, int t
         const int kx = x + pd - st * tx;
         if (kx >= kw) break;
         const float4 v = __ldg(reinterpret_cast<const float4*>(
-            hid + ((f * th + ty) * tw + tx) * hidden + (ky * kw + kx) * C + c));
+            hid + ((static_cast<long long>(b) * th + ty) * tw + tx) * hidden + (ky * kw + kx) * C + c));
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         ++cnt;
       }
     }
     if (normalize) {
-      const float s = 1.f / static_cast<float>(cnt);
-      acc.x *= s; acc.y *= s; acc.z *= s; acc.w *= s;
+      const float sc = 1.f / static_cast<float>(cnt);
+      acc.x *= sc; acc.y *= sc; acc.z *= sc; acc.w *= sc;
     }
-    const long long o = pix * C + c;
+    const long long o = ((static_cast<long long>(b) * OH + y) * OW + x) * C + c;
     if (add) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(add + o));
-      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+      const float4 a4 = __ldg(reinterpret_cast<const float4*>(add + o));
+      acc.x += a4.x; acc.y += a4.y; acc.z += a4.z; acc.w += a4.w;
     }
     if (out) *reinterpret_cast<float4*>(out + o) = acc;
     if (hi) store_split4(hi + o, hi + plane + o, acc.x, acc.y, acc.z, acc.w);
@@ -301,30 +304,32 @@ __global__ void fold_kernel(const float* __restrict__ hid, int bt, int th, int t
 }
 
 // unfold (+ReLU): feature map -> per-token patches, split-bf16 (nn.Unfold + ReLU, ffn_base.py:57-75,40).
+// One block = one token; threadIdx.x = float4 channel group, threadIdx.y strides over the kh*kw positions.
 __global__ void unfold_kernel(const float* __restrict__ img, int bt, int th, int tw, int C, int kh, int kw, int st,
                               int pd, int OH, int OW, int relu, __nv_bfloat16* __restrict__ hi, long long plane) {
   const int C4 = C / 4;
+  if (threadIdx.x >= C4) return;
   const int P = kh * kw;
-  const long long total = static_cast<long long>(bt) * th * tw * P * C4;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % C4) * 4;
-    long long r = i / C4;
-    const int pidx = static_cast<int>(r % P);
-    r /= P;
-    const int tx = static_cast<int>(r % tw);
-    const int ty = static_cast<int>((r / tw) % th);
-    const long long f = r / (static_cast<long long>(tw) * th);
-    const int y = ty * st + pidx / kw - pd;
-    const int x = tx * st + pidx % kw - pd;
+  const int tok = blockIdx.x;
+  const int b = tok / (th * tw);
+  const int rem = tok - b * th * tw;
+  const int ty = rem / tw, tx = rem - ty * tw;
+  const int c = threadIdx.x * 4;
+  int ky = threadIdx.y / kw, kx = threadIdx.y - ky * kw;  // advanced incrementally below
+  const int dky = blockDim.y / kw, dkx = blockDim.y - dky * kw;
+  for (int pidx = threadIdx.y; pidx < P; pidx += blockDim.y) {
+    const int y = ty * st + ky - pd, x = tx * st + kx - pd;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (y >= 0 && y < OH && x >= 0 && x < OW)
-      v = __ldg(reinterpret_cast<const float4*>(img + ((f * OH + y) * OW + x) * C + c));
+      v = __ldg(reinterpret_cast<const float4*>(img + ((static_cast<long long>(b) * OH + y) * OW + x) * C + c));
     if (relu) {
       v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
     }
-    const long long o = i * 4;  // == ((f*th+ty)*tw+tx)*P*C + pidx*C + c
+    const long long o = (static_cast<long long>(tok) * P + pidx) * C + c;
     store_split4(hi + o, hi + plane + o, v.x, v.y, v.z, v.w);
+    ky += dky;
+    kx += dkx;
+    if (kx >= kw) { kx -= kw; ++ky; }
   }
 }
 
@@ -378,8 +383,9 @@ extern "C" int fgt_im2col_nchw(const float* src0, int c0, const float* src1, int
   FGT_REQUIRE(src0 && c0 >= 1 && (c1 == 0 || src1) && cpad % 8 == 0 && k * k * (c0 + c1) <= cpad && k >= 1 &&
                   stride >= 1,
               FGT_ERR_ARG, "im2col_nchw: k=%d cin=%d cpad=%d", k, c0 + c1, cpad);
-  const long long total = static_cast<long long>(n) * OH * OW * (cpad / 8);
-  im2col_nchw_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  FGT_REQUIRE(cpad <= 256, FGT_ERR_ARG, "im2col_nchw: cpad=%d > 256", cpad);
+  const dim3 blk(cpad / 8, 256 / (cpad / 8));
+  im2col_nchw_kernel<<<n * OH, blk, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       src0, c0, src1, c1, n, H, W, k, stride, pad, replicate, OH, OW, cpad, scale, shift,
       reinterpret_cast<__nv_bfloat16*>(out_hi), out_plane);
   FGT_CUDA(cudaGetLastError());
@@ -427,8 +433,10 @@ extern "C" int fgt_fold(const float* hid, int bt, int th, int tw, int C, int kh,
                         int OW, int normalize, const float* add, float* out, void* out_hi, long long out_plane,
                         fgt_stream_t stream) {
   FGT_REQUIRE(hid && C % 4 == 0 && (out || out_hi), FGT_ERR_ARG, "fold: C=%d", C);
-  const long long total = static_cast<long long>(bt) * OH * OW * (C / 4);
-  fold_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  FGT_REQUIRE(C / 4 <= 64, FGT_ERR_ARG, "fold: C=%d > 256", C);
+  const int gx = (C / 4 + 1) / 2 * 2;  // channel groups per row of the thread block
+  const dim3 blk(gx, 256 / gx);
+  fold_kernel<<<bt * OH, blk, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       hid, bt, th, tw, C, kh, kw, stride, pad, OH, OW, normalize, add, out, reinterpret_cast<__nv_bfloat16*>(out_hi),
       out_plane);
   FGT_CUDA(cudaGetLastError());
@@ -438,8 +446,10 @@ extern "C" int fgt_fold(const float* hid, int bt, int th, int tw, int C, int kh,
 extern "C" int fgt_unfold(const float* img, int bt, int th, int tw, int C, int kh, int kw, int stride, int pad,
                           int OH, int OW, int relu, void* out_hi, long long out_plane, fgt_stream_t stream) {
   FGT_REQUIRE(img && out_hi && C % 4 == 0, FGT_ERR_ARG, "unfold: C=%d", C);
-  const long long total = static_cast<long long>(bt) * th * tw * kh * kw * (C / 4);
-  unfold_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  FGT_REQUIRE(C / 4 <= 64, FGT_ERR_ARG, "unfold: C=%d > 256", C);
+  const int gx = (C / 4 + 1) / 2 * 2;
+  const dim3 blk(gx, 256 / gx);
+  unfold_kernel<<<bt * th * tw, blk, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       img, bt, th, tw, C, kh, kw, stride, pad, OH, OW, relu, reinterpret_cast<__nv_bfloat16*>(out_hi), out_plane);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;
