@@ -194,7 +194,7 @@ def main():
         return
     assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
     import torch.distributed as dist
-    from fgt_b200 import lib
+    from fgt_b200 import lib, parallel
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -231,10 +231,7 @@ def main():
             barrier()
             launches = lib.COUNTERS["launches"] - l0
         total_ms = sum(a.elapsed_time(b) for a, b in evs)
-        tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return tt.item() / args.steps, launches
+        return parallel.max_over_ranks(total_ms, dev) / args.steps, launches
 
     def step_device():
         model(*devin)
