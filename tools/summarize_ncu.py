@@ -43,66 +43,59 @@ if os.path.exists(lp):
     with open(os.path.join(PR, f"{tag}_launches.md"), "w") as fh:
         fh.write(f"# ncu launch list, one bench.py step ({len(rows)} launches of fgt:: kernels, {tot:.0f} us serialised)\n\n")
         fh.write("command: `ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled "
-                 "-k regex:fgt:: -s 390 -c 130 --csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline`\n\n")
+                 "-k regex:fgt:: -s 375 -c 125 --csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline`\n\n")
         fh.write("Per-launch times under ncu are cold-cache and serialised: compare SHARES with bench.py's "
                  "`kernels` block, not absolutes.\n\n| kernel | launches | us | share |\n|---|---:|---:|---:|\n")
         for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             fh.write(f"| {k} | {a[0]} | {a[1]:.1f} | {a[1] / tot:.3f} |\n")
     print("wrote", f"{tag}_launches.md")
 
-# ---------------------------------------------------------------- full-set capture
-rp = os.path.join(GO, f"model_{tag}.ncu-rep")
-if os.path.exists(rp):
-    raw = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(raw)))
-    hdr = rows[0]
-    ix = {h: i for i, h in enumerate(hdr)}
-    want = [("Kernel Name", "kernel"), ("Grid Size", "grid"), ("gpu__time_duration.sum", "time_us"),
-            ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pipe_pct"),
-            ("dram__bytes_read.sum", "dram_read_MB"), ("dram__bytes_write.sum", "dram_write_MB"),
-            ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2_pct"),
-            ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram_pct"),
-            ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm_pct"),
-            ("launch__registers_per_thread", "regs"), ("sm__cycles_elapsed.avg.per_second", "sm_ghz")]
-    units = rows[1]
-
-    def conv(col, val):
-        try:
-            x = float(val.replace(",", ""))
-        except ValueError:
-            return val
-        u = units[ix[col]]
-        if col.startswith("dram__bytes"):
-            scale = {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(u, 1.0)
-            return round(x * scale, 3)
-        if col.startswith("gpu__time"):
-            scale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3}.get(u, 1.0)
-            return round(x * scale, 2)
-        return round(x, 3)
-
-    out = []
-    traffic = collections.defaultdict(lambda: [0, 0.0])
-    for r in rows[2:]:
-        if len(r) != len(hdr):
-            continue
-        rec = {}
-        for col, name in want:
-            if col in ix:
-                rec[name] = conv(col, r[ix[col]]) if col not in ("Kernel Name", "Grid Size") else short(r[ix[col]])
-        out.append(rec)
-        t = traffic[rec["kernel"]]
-        t[0] += 1
-        t[1] += (rec.get("dram_read_MB", 0) + rec.get("dram_write_MB", 0)) * 1e6
+# ---------------------------------------------------------------- per-launch hardware metrics of one forward
+# (ncu --metrics ... --csv long format: one row per (launch, metric); small enough to travel, unlike a
+#  --set full .ncu-rep of all 125 launches)
+mp = os.path.join(GO, f"model_metrics_{tag}.csv")
+if os.path.exists(mp):
+    lines = open(mp).read().splitlines()
+    i = [n for n, l in enumerate(lines) if l.startswith('"ID"')][0]
+    rows = list(csv.DictReader(io.StringIO("\n".join(lines[i:]))))
+    per = collections.OrderedDict()
+    for r in rows:
+        d = per.setdefault(r["ID"], {"kernel": short(r["Kernel Name"])})
+        v = float(r["Metric Value"].replace(",", ""))
+        u = r["Metric Unit"]
+        name = r["Metric Name"]
+        if name.startswith("dram__bytes"):
+            v *= {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(u, 1e-6)
+            name = "dram_read_MB" if "read" in name else "dram_write_MB"
+        elif name.startswith("gpu__time"):
+            v *= {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3}.get(u, 1e-3)
+            name = "time_us"
+        else:
+            name = {"sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active": "tensor_pipe_pct",
+                    "lts__throughput.avg.pct_of_peak_sustained_elapsed": "l2_pct",
+                    "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_pct",
+                    "launch__registers_per_thread": "regs"}.get(name, name)
+        d[name] = round(v, 3)
+    fields = ["kernel", "time_us", "tensor_pipe_pct", "dram_read_MB", "dram_write_MB", "l2_pct", "sm_pct", "regs"]
     with open(os.path.join(PR, f"{tag}_ncu_kernels.csv"), "w", newline="") as fh:
-        w = csv.DictWriter(fh, fieldnames=[n for _, n in want])
+        w = csv.DictWriter(fh, fieldnames=fields, extrasaction="ignore")
         w.writeheader()
-        for rec in out:
-            w.writerow(rec)
+        for d in per.values():
+            w.writerow(d)
+    traffic = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0])
+    for d in per.values():
+        k = d["kernel"]
+        key = "gemm_tc" if "gemm_tc" in k else ("flash" if "flash" in k else k.replace("_kernel", ""))
+        t = traffic[key]
+        t[0] += 1
+        t[1] += (d.get("dram_read_MB", 0) + d.get("dram_write_MB", 0)) * 1e6
+        t[2] += d.get("time_us", 0)
+        t[3] += d.get("tensor_pipe_pct", 0) * d.get("time_us", 0)
     tj = {}
-    for k, (n, b) in traffic.items():
-        key = "gemm_tc" if "gemm_tc" in k else ("flash" if "flash" in k else k)
-        tj[key] = {"launches": n, "dram_bytes_total": b, "dram_bytes_per_launch": b / n,
-                   "source": f"profiles/{tag}_ncu_kernels.csv (ncu --set full, one FGT forward 432x240 T=10)"}
+    for k, (n, b, us, tp) in traffic.items():
+        tj[k] = {"launches": n, "dram_bytes_total": b, "dram_bytes_per_launch": b / n, "time_us_total": round(us, 1),
+                 "tensor_pipe_pct_time_weighted": round(tp / us, 2) if us else None,
+                 "source": f"profiles/{tag}_ncu_kernels.csv (ncu --metrics, one FGT forward 432x240 T=10)"}
     with open(os.path.join(PR, "traffic.json"), "w") as fh:
         json.dump(tj, fh, indent=1)
-    print("wrote", f"{tag}_ncu_kernels.csv", "and traffic.json;", len(out), "launches")
+    print("wrote", f"{tag}_ncu_kernels.csv and traffic.json;", len(per), "launches")
