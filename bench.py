@@ -201,6 +201,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     model, sd = build_model(dev)
+    model.net.enable_cuda_graph(True)  # public option: whole forward replayed as one CUDA graph per geometry
     clip = synth.fgt_inputs(seed=3 + rank, t=T, H=H, W=W)
     host = [t.contiguous().pin_memory() for t in clip]
     devin = [t.to(dev) for t in host]
@@ -249,6 +250,7 @@ def main():
 
     # per-kernel breakdown: CUDA events around every launch of 3 more forwards (not part of `value`)
     peaks = load_peaks()
+    model.net.enable_cuda_graph(False)  # per-launch CUDA events need the eager launch sequence
     lib.profile_start()
     with torch.no_grad():
         for _ in range(3):
@@ -306,6 +308,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate)",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": T, "parallelism": f"window-dp{world}",
+                       "cuda_graph": True,
                        "l2": "256 MiB buffer rewritten between steps (untimed); activations (>1 GB) exceed L2"},
             "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},

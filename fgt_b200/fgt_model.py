@@ -500,9 +500,20 @@ class FGT(nn.Module):
         self._ffn(g, P, name, x, xs, dev)
 
     # ------------------------------------------------------------------ forward
+    def enable_cuda_graph(self, on=True):
+        """Replay the whole forward as one CUDA graph per input geometry (fgt_b200/graphs.py)."""
+        from .graphs import GraphedCall
+        self._graphed = GraphedCall(self._forward_impl) if on else None
+
     def forward(self, masked_frames, flows, masks):
         if not masked_frames.is_cuda:
             raise RuntimeError("fgt_b200.FGT runs on a CUDA (sm_100a) device only; there is no CPU fallback")
+        if getattr(self, "_graphed", None) is not None and self.capture is None:
+            return self._graphed(masked_frames.float().contiguous(), flows.float().contiguous(),
+                                 masks.float().contiguous())
+        return self._forward_impl(masked_frames, flows, masks)
+
+    def _forward_impl(self, masked_frames, flows, masks):
         dev = masked_frames.device
         b, t, c, H, W = masked_frames.shape
         bt = b * t

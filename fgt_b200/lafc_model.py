@@ -220,11 +220,21 @@ class P3DNet(nn.Module):
         ops.conv([(e2_, 16)], P["edge_o"], act=lib.ACT_SIGMOID, out_f32=edge, nchw_out=True)
         return flow, edge
 
+    def enable_cuda_graph(self, on=True):
+        """Replay the whole forward as one CUDA graph per input geometry (fgt_b200/graphs.py)."""
+        from .graphs import GraphedCall
+        self._graphed = GraphedCall(self._forward_impl) if on else None
+
     def forward(self, flows, masks, edges=None):
         if edges is not None:
             raise ValueError("fgt_b200 LAFC: the `edges` input is unused by the shipped driver (always None)")
         if not flows.is_cuda:
             raise RuntimeError("fgt_b200 LAFC runs on a CUDA (sm_100a) device only; there is no CPU fallback")
+        if getattr(self, "_graphed", None) is not None:
+            return self._graphed(flows.float().contiguous(), masks.float().contiguous())
+        return self._forward_impl(flows, masks)
+
+    def _forward_impl(self, flows, masks):
         b, _, T, H, W = flows.shape
         if T != self.T or H % 4 or W % 4:
             raise ValueError(f"LAFC input [T={T},{H}x{W}]: T must be {self.T} and H, W divisible by 4")

@@ -318,9 +318,24 @@ class RAFT(nn.Module):
                 ups.append(up)
         return flow_nchw.clone(), ups
 
+    def enable_cuda_graph(self, on=True):
+        """Replay whole forwards as CUDA graphs, one per (geometry, iters, test_mode) (fgt_b200/graphs.py)."""
+        self._graphs = {} if on else None
+
     def forward(self, image1, image2, iters=12, flow_init=None, upsample=True, test_mode=False):
         if not image1.is_cuda:
             raise RuntimeError("fgt_b200 RAFT runs on a CUDA (sm_100a) device only; there is no CPU fallback")
+        if getattr(self, "_graphs", None) is not None and flow_init is None:
+            from .graphs import GraphedCall
+            key = (iters, bool(test_mode))
+            if key not in self._graphs:
+                self._graphs[key] = GraphedCall(
+                    lambda a, b, _it=iters, _tm=test_mode: self._forward_impl(a, b, _it, None, _tm))
+            out = self._graphs[key](image1.float().contiguous(), image2.float().contiguous())
+            return list(out) if not test_mode else out
+        return self._forward_impl(image1, image2, iters, flow_init, test_mode)
+
+    def _forward_impl(self, image1, image2, iters, flow_init, test_mode):
         dev = image1.device
         P = self._packed if self._packed is not None else self._pack(dev)
         image1, image2 = image1.float().contiguous(), image2.float().contiguous()

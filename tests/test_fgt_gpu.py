@@ -73,3 +73,22 @@ def test_fgt_batch2_and_odd_t():
     with torch.no_grad():
         out2 = model(fr.cuda(), fl.cuda(), mk.cuda())
     assert torch.equal(out, out2)
+
+
+def test_fgt_720p_padded_geometry():
+    """BASELINE config 5 geometry (720x1280): tokens 60x107 -> temporal zones padded by one column,
+    spatial grid padded to 64x112 (112 windows, 448 pooled tokens = 7 global key tiles). T=2 keeps the
+    CPU oracle to a few seconds."""
+    from oracle import fgt_oracle as O
+    from fgt_b200.fgt_model import Model
+    cfg = dict(synth.CFG_A)
+    sd = synth.make_state_dict(synth.fgt_param_shapes(cfg), seed=6)
+    model = Model(cfg)
+    model.load_state_dict(sd)
+    model = model.cuda()
+    fr, fl, mk = synth.fgt_inputs(seed=11, t=2, H=720, W=1280)
+    with torch.no_grad():
+        out = model(fr.cuda(), fl.cuda(), mk.cuda())
+        ref = O.fgt_forward(O.strip_net(sd), fr, fl, mk)
+    assert tuple(out.shape) == (2, 3, 720, 1280)
+    assert_close(out, ref, REL_TOL, "720p T=2")
