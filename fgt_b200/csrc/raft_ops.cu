@@ -21,62 +21,92 @@ static int grid_cap(long long work_items, int block) {
 // RAFT/extractor.py:29-33,131-132). Block = 256 threads covering `C` channels x row slices; fp32
 // partials over <=64 rows, double atomics across blocks.
 // ------------------------------------------------------------------------------------------
-__global__ void chan_stats_kernel(const float* __restrict__ x, int HW, int C, int rows_per_block,
-                                  double* __restrict__ stats) {
+__global__ void __launch_bounds__(512) chan_stats_kernel(const float* __restrict__ x, int HW, int C,
+                                                         int rows_per_block, double* __restrict__ stats) {
+  __shared__ float red_s[512], red_q[512];
   const int img = blockIdx.y;
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(r0 + rows_per_block, HW);
   const float* base = x + static_cast<long long>(img) * HW * C;
-  const int lanes_per_row = C;  // thread t handles channel t % C, rows strided by blockDim/C
-  const int c = threadIdx.x % lanes_per_row;
-  const int rstep = blockDim.x / lanes_per_row;
+  const int rstep = blockDim.x / C;       // row slots per block; thread t: channel t % C, slot t / C
+  const int c = threadIdx.x % C;
+  const int slot = threadIdx.x / C;
   float s = 0.f, q = 0.f;
-  for (int r = r0 + threadIdx.x / lanes_per_row; r < r1; r += rstep) {
-    const float v = base[static_cast<long long>(r) * C + c];
-    s += v;
-    q += v * v;
+  if (slot < rstep) {
+    int r = r0 + slot;
+    // eight independent loads in flight per thread (one at a time is latency bound)
+    for (; r + 7 * rstep < r1; r += 8 * rstep) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __ldg(base + static_cast<long long>(r + j * rstep) * C + c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s += v[j]; q += v[j] * v[j]; }
+    }
+    for (; r < r1; r += rstep) {
+      const float v = __ldg(base + static_cast<long long>(r) * C + c);
+      s += v;
+      q += v * v;
+    }
   }
-  if (threadIdx.x < rstep * lanes_per_row) {
-    atomicAdd(&stats[(static_cast<long long>(img) * C + c) * 2], static_cast<double>(s));
-    atomicAdd(&stats[(static_cast<long long>(img) * C + c) * 2 + 1], static_cast<double>(q));
+  red_s[threadIdx.x] = s;
+  red_q[threadIdx.x] = q;
+  __syncthreads();
+  // one pair of atomics per (block, channel): same-address double atomics serialise at ~25 ns each,
+  // which dominated the first version (4 row slots x 405 blocks per address)
+  if (threadIdx.x < C) {
+    double ds = 0.0, dq = 0.0;
+    for (int j = 0; j < rstep; ++j) {
+      ds += static_cast<double>(red_s[j * C + c]);
+      dq += static_cast<double>(red_q[j * C + c]);
+    }
+    atomicAdd(&stats[(static_cast<long long>(img) * C + c) * 2], ds);
+    atomicAdd(&stats[(static_cast<long long>(img) * C + c) * 2 + 1], dq);
   }
 }
 
 // y = (x - mean) * rstd ; optional ReLU ; optional residual: y = relu(y + res). fp32 and/or split out.
-__global__ void instnorm_act_kernel(const float* __restrict__ x, const double* __restrict__ stats, int n, int HW,
-                                    int C, float eps, int relu, const float* __restrict__ res,
-                                    float* __restrict__ out, __nv_bfloat16* __restrict__ hi, long long plane) {
+// grid.y = image; per-channel scale / shift are derived once per block from the double statistics.
+__global__ void instnorm_act_kernel(const float* __restrict__ x, const double* __restrict__ stats, int HW, int C,
+                                    float eps, int relu, const float* __restrict__ res, float* __restrict__ out,
+                                    __nv_bfloat16* __restrict__ hi, long long plane) {
+  __shared__ float sc[256], sh[256];
+  const int img = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double su = stats[(static_cast<long long>(img) * C + c) * 2];
+    const double sq = stats[(static_cast<long long>(img) * C + c) * 2 + 1];
+    const double mean = su / HW;
+    const double var = fmax(sq / HW - mean * mean, 0.0);  // biased variance, like InstanceNorm2d
+    const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    sc[c] = rstd;
+    sh[c] = static_cast<float>(mean);
+  }
+  __syncthreads();
   const int C4 = C / 4;
-  const long long total = static_cast<long long>(n) * HW * C4;
+  const long long total = static_cast<long long>(HW) * C4;
+  const long long img_off = static_cast<long long>(img) * HW * C;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % C4) * 4;
-    const long long pix = i / C4;
-    const int img = static_cast<int>(pix / HW);
-    const float4 v = __ldg(reinterpret_cast<const float4*>(x + pix * C + c));
-    float o[4] = {v.x, v.y, v.z, v.w};
+    const long long off = img_off + (i / C4) * C + c;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + off));
+    float o[4] = {(v.x - sh[c]) * sc[c], (v.y - sh[c + 1]) * sc[c + 1], (v.z - sh[c + 2]) * sc[c + 2],
+                  (v.w - sh[c + 3]) * sc[c + 3]};
+    if (relu) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const double su = stats[(static_cast<long long>(img) * C + c + j) * 2];
-      const double sq = stats[(static_cast<long long>(img) * C + c + j) * 2 + 1];
-      const double mean = su / HW;
-      const double var = fmax(sq / HW - mean * mean, 0.0);  // biased variance, like InstanceNorm2d
-      const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-      o[j] = (o[j] - static_cast<float>(mean)) * rstd;
-      if (relu) o[j] = fmaxf(o[j], 0.f);
+      for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.f);
     }
     if (res) {
-      const float4 r = __ldg(reinterpret_cast<const float4*>(res + pix * C + c));
+      const float4 r = __ldg(reinterpret_cast<const float4*>(res + off));
       o[0] = fmaxf(o[0] + r.x, 0.f); o[1] = fmaxf(o[1] + r.y, 0.f);
       o[2] = fmaxf(o[2] + r.z, 0.f); o[3] = fmaxf(o[3] + r.w, 0.f);
     }
-    const long long off = pix * C + c;
     if (out) *reinterpret_cast<float4*>(out + off) = make_float4(o[0], o[1], o[2], o[3]);
     if (hi) {
-      __nv_bfloat16 h0, l0, h1, l1, h2, l2, h3, l3;
-      split_bf16(o[0], h0, l0); split_bf16(o[1], h1, l1); split_bf16(o[2], h2, l2); split_bf16(o[3], h3, l3);
-      *reinterpret_cast<uint2*>(hi + off) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
-      *reinterpret_cast<uint2*>(hi + plane + off) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+      uint32_t h0, l0, h1, l1;
+      split_bf16x2(o[0], o[1], h0, l0);
+      split_bf16x2(o[2], o[3], h1, l1);
+      *reinterpret_cast<uint2*>(hi + off) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(hi + plane + off) = make_uint2(l0, l1);
     }
   }
 }
@@ -156,11 +186,12 @@ __global__ void corr_lookup_kernel(LookupLevels lv, int levels, int radius, cons
 // coords1 += delta (raft.py:132); emits flow = coords1 - coords0 (coords0 = pixel grid, raft.py:64-71)
 // as NCHW fp32 (input of the 7x7 flow conv) and as the last two channels of the GRU input buffer x.
 // ------------------------------------------------------------------------------------------
-__global__ void flow_update_kernel(float* __restrict__ coords, const float* __restrict__ delta, int h, int w,
-                                   float* __restrict__ flow_nchw, __nv_bfloat16* __restrict__ x_hi, long long x_plane,
-                                   int x_pitch, int x_chan) {
+__global__ void flow_update_kernel(float* __restrict__ coords, const float* __restrict__ delta, int n_img, int h,
+                                   int w, float* __restrict__ flow_nchw, __nv_bfloat16* __restrict__ x_hi,
+                                   long long x_plane, int x_pitch, int x_chan) {
   const int n = h * w;
-  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_img * n; p += gridDim.x * blockDim.x) {
+    const int img = p / n, q = p - img * n;
     float cx = coords[2 * p], cy = coords[2 * p + 1];
     if (delta) {
       cx += delta[2 * p];
@@ -168,9 +199,9 @@ __global__ void flow_update_kernel(float* __restrict__ coords, const float* __re
       coords[2 * p] = cx;
       coords[2 * p + 1] = cy;
     }
-    const float fx = cx - static_cast<float>(p % w), fy = cy - static_cast<float>(p / w);
-    flow_nchw[p] = fx;
-    flow_nchw[n + p] = fy;
+    const float fx = cx - static_cast<float>(q % w), fy = cy - static_cast<float>(q / w);
+    flow_nchw[static_cast<long long>(img) * 2 * n + q] = fx;
+    flow_nchw[static_cast<long long>(img) * 2 * n + n + q] = fy;
     if (x_hi) {
       __nv_bfloat16 h0, l0, h1, l1;
       split_bf16(fx, h0, l0);
@@ -185,18 +216,21 @@ __global__ void flow_update_kernel(float* __restrict__ coords, const float* __re
 // ------------------------------------------------------------------------------------------
 // Convex 8x upsampling (RAFT.upsample_flow, raft.py:73-84): softmax over the 9 mask logits of every
 // fine pixel, weighted sum of the 3x3 neighbourhood of 8*flow (zero padded).
-// mask: [h*w, 576] fp32 with channel = k*64 + i*8 + j; out: [2, 8h, 8w] fp32.
+// mask: [n_img*h*w, 576] fp32 with channel = k*64 + i*8 + j; flow: [n_img, 2, h, w]; out: [n_img, 2, 8h, 8w] fp32.
 // ------------------------------------------------------------------------------------------
-__global__ void convex_upsample_kernel(const float* __restrict__ mask, const float* __restrict__ flow_nchw, int h,
-                                       int w, float* __restrict__ out) {
-  const long long total = static_cast<long long>(h) * w * 64;
+__global__ void convex_upsample_kernel(const float* __restrict__ mask, const float* __restrict__ flow_all, int n_img,
+                                       int h, int w, float* __restrict__ out_all) {
   const int n = h * w;
+  const long long total = static_cast<long long>(n_img) * n * 64;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int sub = static_cast<int>(i & 63);
-    const int p = static_cast<int>(i >> 6);
+    const int pg = static_cast<int>(i >> 6);
+    const int img = pg / n, p = pg - img * n;
     const int y = p / w, x = p - y * w;
-    const float* m = mask + static_cast<long long>(p) * 576 + sub;
+    const float* flow_nchw = flow_all + static_cast<long long>(img) * 2 * n;
+    float* out = out_all + static_cast<long long>(img) * 128 * n;
+    const float* m = mask + static_cast<long long>(pg) * 576 + sub;
     float logit[9], mx = -INFINITY;
 #pragma unroll
     for (int k = 0; k < 9; ++k) {
@@ -229,9 +263,14 @@ extern "C" int fgt_chan_stats(const float* x, int n, int HW, int C, double* stat
   FGT_REQUIRE(x && stats && C >= 1 && C <= 256, FGT_ERR_ARG, "chan_stats: C=%d", C);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   FGT_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * n * C, st));
-  const int rows_per_block = 64 * (256 / C);
+  // about two blocks per SM over all images; each block reduces its rows in shared memory first
+  int blocks_x = (2 * num_sms() + n - 1) / n;
+  const int rstep = 512 / C;
+  int rows_per_block = (HW + blocks_x - 1) / blocks_x;
+  rows_per_block = ((rows_per_block + rstep - 1) / rstep) * rstep;
+  if (rows_per_block < 8 * rstep) rows_per_block = 8 * rstep;
   dim3 grid((HW + rows_per_block - 1) / rows_per_block, n);
-  chan_stats_kernel<<<grid, 256, 0, st>>>(x, HW, C, rows_per_block, stats);
+  chan_stats_kernel<<<grid, 512, 0, st>>>(x, HW, C, rows_per_block, stats);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;
 }
@@ -240,9 +279,11 @@ extern "C" int fgt_instnorm_act(const float* x, const double* stats, int n, int 
                                 const float* res, float* out, void* out_hi, long long out_plane,
                                 fgt_stream_t stream) {
   FGT_REQUIRE(x && stats && C % 4 == 0 && (out || out_hi), FGT_ERR_ARG, "instnorm_act: C=%d", C);
-  const long long total = static_cast<long long>(n) * HW * (C / 4);
-  instnorm_act_kernel<<<grid_cap(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, stats, n, HW, C, eps, relu, res, out, reinterpret_cast<__nv_bfloat16*>(out_hi), out_plane);
+  FGT_REQUIRE(C <= 256, FGT_ERR_ARG, "instnorm_act: C=%d > 256", C);
+  const long long total = static_cast<long long>(HW) * (C / 4);
+  const dim3 grid(grid_cap(total, 256), n);
+  instnorm_act_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, stats, HW, C, eps, relu, res, out, reinterpret_cast<__nv_bfloat16*>(out_hi), out_plane);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;
 }
@@ -277,21 +318,22 @@ extern "C" int fgt_corr_lookup(const float* const* level_ptrs_host, const int* l
   return FGT_OK;
 }
 
-extern "C" int fgt_raft_flow_update(float* coords, const float* delta, int h, int w, float* flow_nchw, void* x_hi,
-                                    long long x_plane, int x_pitch, int x_chan, fgt_stream_t stream) {
-  FGT_REQUIRE(coords && flow_nchw, FGT_ERR_ARG, "raft_flow_update: null argument");
-  flow_update_kernel<<<grid_cap(static_cast<long long>(h) * w, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      coords, delta, h, w, flow_nchw, reinterpret_cast<__nv_bfloat16*>(x_hi), x_plane, x_pitch, x_chan);
+extern "C" int fgt_raft_flow_update(float* coords, const float* delta, int n, int h, int w, float* flow_nchw,
+                                    void* x_hi, long long x_plane, int x_pitch, int x_chan, fgt_stream_t stream) {
+  FGT_REQUIRE(coords && flow_nchw && n >= 1, FGT_ERR_ARG, "raft_flow_update: null argument");
+  flow_update_kernel<<<grid_cap(static_cast<long long>(n) * h * w, 256), 256, 0,
+                       reinterpret_cast<cudaStream_t>(stream)>>>(
+      coords, delta, n, h, w, flow_nchw, reinterpret_cast<__nv_bfloat16*>(x_hi), x_plane, x_pitch, x_chan);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;
 }
 
-extern "C" int fgt_convex_upsample(const float* mask, const float* flow_nchw, int h, int w, float* out,
+extern "C" int fgt_convex_upsample(const float* mask, const float* flow_nchw, int n, int h, int w, float* out,
                                    fgt_stream_t stream) {
-  FGT_REQUIRE(mask && flow_nchw && out, FGT_ERR_ARG, "convex_upsample: null argument");
-  const long long total = static_cast<long long>(h) * w * 64;
-  convex_upsample_kernel<<<grid_cap(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(mask, flow_nchw, h,
-                                                                                                w, out);
+  FGT_REQUIRE(mask && flow_nchw && out && n >= 1, FGT_ERR_ARG, "convex_upsample: null argument");
+  const long long total = static_cast<long long>(n) * h * w * 64;
+  convex_upsample_kernel<<<grid_cap(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      mask, flow_nchw, n, h, w, out);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;
 }

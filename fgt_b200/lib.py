@@ -90,8 +90,8 @@ def load():
     lib.fgt_avgpool2.argtypes = [_c_p, cll, ci, ci, _c_p, _c_p]
     lib.fgt_corr_lookup.argtypes = [ctypes.POINTER(_c_p), ctypes.POINTER(ci), ctypes.POINTER(ci), ci, ci, _c_p, ci,
                                     ci, _c_p, cll, _c_p]
-    lib.fgt_raft_flow_update.argtypes = [_c_p, _c_p, ci, ci, _c_p, _c_p, cll, ci, ci, _c_p]
-    lib.fgt_convex_upsample.argtypes = [_c_p, _c_p, ci, ci, _c_p, _c_p]
+    lib.fgt_raft_flow_update.argtypes = [_c_p, _c_p, ci, ci, ci, _c_p, _c_p, cll, ci, ci, _c_p]
+    lib.fgt_convex_upsample.argtypes = [_c_p, _c_p, ci, ci, ci, _c_p, _c_p]
     for fn in (lib.fgt_chan_stats, lib.fgt_instnorm_act, lib.fgt_avgpool2, lib.fgt_corr_lookup,
                lib.fgt_raft_flow_update, lib.fgt_convex_upsample):
         fn.restype = ctypes.c_int
@@ -370,15 +370,15 @@ def corr_lookup(levels, coords, n_pix, radius, out_split, tag=""):
                                      _dp(out_split), plane_elems(out_split), stream_ptr()), "fgt_corr_lookup")
 
 
-def raft_flow_update(coords, delta, h, w, flow_nchw, x_split=None, x_chan=0, tag=""):
-    with _Prof("raft_flow_update", tag, 0, 32.0 * h * w):
-        check(load().fgt_raft_flow_update(_dp(coords), _dp(delta), h, w, _dp(flow_nchw), _dp(x_split),
+def raft_flow_update(coords, delta, h, w, flow_nchw, x_split=None, x_chan=0, n=1, tag=""):
+    with _Prof("raft_flow_update", tag, 0, 32.0 * n * h * w):
+        check(load().fgt_raft_flow_update(_dp(coords), _dp(delta), n, h, w, _dp(flow_nchw), _dp(x_split),
                                           plane_elems(x_split) if x_split is not None else 0,
                                           x_split.shape[-1] if x_split is not None else 0, x_chan, stream_ptr()),
               "fgt_raft_flow_update")
 
 
-def convex_upsample(mask, flow_nchw, h, w, out, tag=""):
-    with _Prof("convex_upsample", tag, 0, 4.0 * h * w * (576 + 128)):
-        check(load().fgt_convex_upsample(_dp(mask), _dp(flow_nchw), h, w, _dp(out), stream_ptr()),
+def convex_upsample(mask, flow_nchw, h, w, out, n=1, tag=""):
+    with _Prof("convex_upsample", tag, 0, 4.0 * n * h * w * (576 + 128)):
+        check(load().fgt_convex_upsample(_dp(mask), _dp(flow_nchw), n, h, w, _dp(out), stream_ptr()),
               "fgt_convex_upsample")

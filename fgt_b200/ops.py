@@ -28,6 +28,15 @@ def pick_bn(n_per_group, groups=1):
     return 128
 
 
+def fill_sms(bn, n_total, m_positions, groups=1, n_sms=148):
+    """Small-M problems (RAFT's 1/8-resolution update block: 51 tiles of 128 positions) leave most SMs idle
+    with 128-wide channel tiles; halve the tile while that raises the number of busy SMs."""
+    m_tiles = -(-m_positions // 128)
+    while bn >= 128 and bn % 32 == 0 and m_tiles * -(-n_total // bn) < n_sms and (groups == 1 or (n_total // groups) % (bn // 2) == 0):
+        bn //= 2
+    return bn
+
+
 def packed(name, weight, bias, dev, seg_counts=None, im2col_pad=None):
     """Weight record consumed by conv()/linear(): split-bf16 packed weight + fp32 bias."""
     if im2col_pad is not None:
@@ -59,7 +68,8 @@ def conv(xs, wp, *, kx=1, ky=1, kz=1, stride=1, dil=1, pad_x=0, pad_y=0, pad_z=0
         ct = N if out_c_total is None else out_c_total  # write into a channel slice of a wider NHWC buffer
         strides = dict(os_z=oy * ox * ct, os_y=ox * ct, os_x=ct, os_c=1, out_elem_offset=out_c_offset)
     lib.gemm_tc(segs, wp["w"], N, kx=kx, ky=ky, kz=kz, stride=stride, dil=dil, pad_x=pad_x, pad_y=pad_y, pad_z=pad_z,
-                groups=groups, out_w=ox, out_h=oy, out_z=oz, box_w=bw, box_h=bh, bn=pick_bn(N // groups, groups),
+                groups=groups, out_w=ox, out_h=oy, out_z=oz, box_w=bw, box_h=bh,
+                bn=fill_sms(pick_bn(N // groups, groups), N, ox * oy * oz, groups),
                 bias=wp["b"], alpha=alpha, act=act, aux=aux, aux_mode=aux_mode, aux2=aux2, out_f32=out_f32, out_split=out_split,
                 tag=wp["name"], **strides)
     return oz, oy, ox
@@ -68,4 +78,5 @@ def conv(xs, wp, *, kx=1, ky=1, kz=1, stride=1, dil=1, pad_x=0, pad_y=0, pad_z=0
 def linear(segs, wp, rows, **kw):
     """segs: list of (split tensor [2, rows, C], C). Row-major [rows, N] outputs."""
     asegs = [lib.ASeg(t, c, rows) for t, c in segs]
-    lib.gemm_tc(asegs, wp["w"], wp["N"], out_w=rows, bn=pick_bn(wp["N"], 1), bias=wp["b"], tag=wp["name"], **kw)
+    lib.gemm_tc(asegs, wp["w"], wp["N"], out_w=rows, bn=fill_sms(pick_bn(wp["N"], 1), wp["N"], rows),
+                bias=wp["b"], tag=wp["name"], **kw)

@@ -229,71 +229,77 @@ class RAFT(nn.Module):
         return x, hh, ww  # NHWC split [2, n, H/8, W/8, 128]
 
     # ------------------------------------------------------------------ forward
-    def _forward_one(self, im1, im2, iters, flow_init, test_mode, P, dev):
-        _, H, W = im1.shape
+    def _forward_batch(self, im1, im2, iters, flow_init, test_mode, P, dev):
+        """RAFT.forward (raft.py:86-148) on n image pairs at once: every kernel of the update loop covers
+        the n*h*w positions of all pairs, which is what fills the 148 SMs (one 1/8-resolution pair is 51 tiles)."""
+        n, _, H, W = im1.shape
         if H % 8 or W % 8:
             raise ValueError(f"RAFT input {H}x{W} must be divisible by 8 (the reference crashes otherwise, "
                              "RAFT/raft.py:64-71 vs extractor.py)")
         h, w = H // 8, W // 8
         npx = h * w
-        key = ("iter", H, W)
+        tot = n * npx
+        key = ("iter", n, H, W)
         B = lambda nm, s, **kw: self._buf(key, nm, s, dev, **kw)  # noqa: E731
         RELU, SIG, TANH, NONE = lib.ACT_RELU, lib.ACT_SIGMOID, lib.ACT_TANH, lib.ACT_NONE
-        # ---- feature net on both images, 1x1 output conv -> fmaps [2, npx, 256] (split)
-        f128, _, _ = self._encoder(torch.stack([im1, im2], 0), "fnet", P, dev, 2)
-        fmap = B("fmap", (2 * npx, 256))
-        ops.linear([(f128.view(2, 2 * npx, 128), 128)], P["fnet.conv2"], 2 * npx, out_split=fmap)
-        # ---- all-pairs correlation (corr.py:52-60): corr[i,j] = <f1_i, f2_j> / 16, then the pyramid
-        pyr = [B("corr0", (npx, h, w), split=False)]
-        f1 = lib.ASeg(fmap, 256, npx)
-        f2 = fmap[:, npx:]  # view: rows of image 2 as the "weight" operand [N=npx, K=256]
-        lib.gemm_tc([f1], f2, npx, out_w=npx, bn=128, alpha=1.0 / 16.0, out_f32=pyr[0], tag="corr")
+        # ---- feature net on all 2n images, 1x1 output conv -> fmaps [2, 2n*npx, 256] (split)
+        f128, _, _ = self._encoder(torch.cat([im1, im2], 0), "fnet", P, dev, 2 * n)
+        fmap = B("fmap", (2 * tot, 256))
+        ops.linear([(f128.view(2, 2 * tot, 128), 128)], P["fnet.conv2"], 2 * tot, out_split=fmap)
+        # ---- all-pairs correlation (corr.py:52-60): corr[i,j] = <f1_i, f2_j> / 16 per pair, then the pyramid
+        pyr = [B("corr0", (tot, h, w), split=False)]
+        for i in range(n):
+            f1 = lib.ASeg(fmap[:, i * npx:(i + 1) * npx], 256, npx)
+            f2 = fmap[:, (n + i) * npx:(n + i + 1) * npx]  # rows of image 2 as the "weight" operand [N=npx, K=256]
+            lib.gemm_tc([f1], f2, npx, out_w=npx, bn=128, alpha=1.0 / 16.0, out_f32=pyr[0][i * npx:(i + 1) * npx],
+                        tag="corr")
         hh, ww = h, w
         for i in range(1, 4):
-            nxt = B(f"corr{i}", (npx, hh // 2, ww // 2), split=False)
-            lib.avgpool2(pyr[-1], npx, hh, ww, nxt)
+            nxt = B(f"corr{i}", (tot, hh // 2, ww // 2), split=False)
+            lib.avgpool2(pyr[-1], tot, hh, ww, nxt)
             pyr.append(nxt)
             hh, ww = hh // 2, ww // 2
         # ---- context net: net = tanh(c[:128]), inp = relu(c[128:]) (raft.py:112-115)
-        c128, _, _ = self._encoder(im1[None], "cnet", P, dev, 1)
-        hsp = B("h", (npx, 128))
-        hf = B("hf", (npx, 128), split=False)
-        xbuf = B("x", (npx, 256))  # GRU input x = [inp(128) | motion features(126) | flow(2)]
+        c128, _, _ = self._encoder(im1, "cnet", P, dev, n)
+        hsp = B("h", (tot, 128))
+        hf = B("hf", (tot, 128), split=False)
+        xbuf = B("x", (tot, 256))  # GRU input x = [inp(128) | motion features(126) | flow(2)]
         cw = P["cnet.conv2"]
-        w_net = dict(cw, w=cw["w"][:, :128].contiguous(), b=cw["b"][:128].contiguous(), N=128, name="cnet.net")
-        w_inp = dict(cw, w=cw["w"][:, 128:].contiguous(), b=cw["b"][128:].contiguous(), N=128, name="cnet.inp")
-        ops.linear([(c128.view(2, npx, 128), 128)], w_net, npx, act=TANH, out_split=hsp, out_f32=hf)
-        ops.linear([(c128.view(2, npx, 128), 128)], w_inp, npx, act=RELU, out_split=xbuf, os_x=256)
+        if "cnet.net" not in P:
+            P["cnet.net"] = dict(cw, w=cw["w"][:, :128].contiguous(), b=cw["b"][:128].contiguous(), N=128, name="cnet.net")
+            P["cnet.inp"] = dict(cw, w=cw["w"][:, 128:].contiguous(), b=cw["b"][128:].contiguous(), N=128, name="cnet.inp")
+        ops.linear([(c128.view(2, tot, 128), 128)], P["cnet.net"], tot, act=TANH, out_split=hsp, out_f32=hf)
+        ops.linear([(c128.view(2, tot, 128), 128)], P["cnet.inp"], tot, act=RELU, out_split=xbuf, os_x=256)
         # ---- iterations
-        coords = B("coords", (npx, 2), split=False)
+        coords = B("coords", (tot, 2), split=False)
         ys, xs = torch.meshgrid(torch.arange(h, device=dev), torch.arange(w, device=dev), indexing="ij")
-        coords.copy_(torch.stack([xs, ys], -1).reshape(npx, 2).float())
+        coords.view(n, npx, 2).copy_(torch.stack([xs, ys], -1).reshape(1, npx, 2).float().expand(n, npx, 2))
         if flow_init is not None:
-            coords.add_(flow_init.permute(1, 2, 0).reshape(npx, 2).float())
-        flow_nchw = B("flow", (2, h, w), split=False)
-        lib.raft_flow_update(coords, None, h, w, flow_nchw, xbuf, 254)
-        look = B("look", (npx, 384), zero=True)
-        cor1 = B("cor1", (1, h, w, 256))
-        corflo = B("corflo", (1, h, w, 256))  # [cor(192) | flo(64)]
-        fcol = B("fcol", (1, h, w, 128))
-        flo1 = B("flo1", (1, h, w, 128))
-        z = B("z", (npx, 128), split=False)
-        rh = B("rh", (1, h, w, 128))
-        fh = B("fh", (1, h, w, 256))
-        delta = B("delta", (npx, 2), split=False)
-        m0 = B("m0", (1, h, w, 256))
-        mask = B("mask", (npx, 576), split=False)
-        h4 = hsp.view(2, 1, h, w, 128)
-        x4 = xbuf.view(2, 1, h, w, 256)
+            coords.add_(flow_init.permute(0, 2, 3, 1).reshape(tot, 2).float())
+        flow_nchw = B("flow", (n, 2, h, w), split=False)
+        lib.raft_flow_update(coords, None, h, w, flow_nchw, xbuf, 254, n=n)
+        look = B("look", (tot, 384), zero=True)
+        cor1 = B("cor1", (n, h, w, 256))
+        corflo = B("corflo", (n, h, w, 256))  # [cor(192) | flo(64)]
+        fcol = B("fcol", (n, h, w, 128))
+        flo1 = B("flo1", (n, h, w, 128))
+        z = B("z", (tot, 128), split=False)
+        rh = B("rh", (n, h, w, 128))
+        fh = B("fh", (n, h, w, 256))
+        delta = B("delta", (tot, 2), split=False)
+        m0 = B("m0", (n, h, w, 256))
+        mask = B("mask", (tot, 576), split=False)
+        h4 = hsp.view(2, n, h, w, 128)
+        x4 = xbuf.view(2, n, h, w, 256)
         ups = []
         for it in range(iters):
-            lib.corr_lookup(pyr, coords, npx, 4, look)
+            lib.corr_lookup(pyr, coords, tot, 4, look)
             # motion encoder (update.py:89-97)
-            ops.linear([(look, 384)], P["convc1"], npx, act=RELU, out_split=cor1.view(2, npx, 256))
+            ops.linear([(look, 384)], P["convc1"], tot, act=RELU, out_split=cor1.view(2, tot, 256))
             ops.conv([(cor1, 256)], P["convc2"], kx=3, ky=3, pad_x=1, pad_y=1, act=RELU, out_split=corflo,
                      out_c_total=256, out_c_offset=0)
-            lib.im2col_nchw(flow_nchw.view(1, 2, h, w), None, fcol, k=7, stride=1, pad=3, replicate=False, OH=h, OW=w)
-            ops.linear([(fcol.view(2, npx, 128), 128)], P["convf1"], npx, act=RELU, out_split=flo1.view(2, npx, 128))
+            lib.im2col_nchw(flow_nchw, None, fcol, k=7, stride=1, pad=3, replicate=False, OH=h, OW=w)
+            ops.linear([(fcol.view(2, tot, 128), 128)], P["convf1"], tot, act=RELU, out_split=flo1.view(2, tot, 128))
             ops.conv([(flo1, 128)], P["convf2"], kx=3, ky=3, pad_x=1, pad_y=1, act=RELU, out_split=corflo,
                      out_c_total=256, out_c_offset=192)
             ops.conv([(corflo, 256)], P["mconv"], kx=3, ky=3, pad_x=1, pad_y=1, act=RELU, out_split=x4,
@@ -301,20 +307,20 @@ class RAFT(nn.Module):
             # SepConvGRU (update.py:45-60): horizontal (1x5) then vertical (5x1)
             for s, (kx, ky) in (("1", (5, 1)), ("2", (1, 5))):
                 kw = dict(kx=kx, ky=ky, pad_x=kx // 2, pad_y=ky // 2, seg_counts=[128, 256])
-                ops.conv([(h4, 128), (x4, 256)], P[f"gru.z{s}"], act=SIG, out_f32=z.view(1, h, w, 128), **kw)
+                ops.conv([(h4, 128), (x4, 256)], P[f"gru.z{s}"], act=SIG, out_f32=z.view(n, h, w, 128), **kw)
                 ops.conv([(h4, 128), (x4, 256)], P[f"gru.r{s}"], act=SIG, aux=hf, aux_mode=lib.AUX_MUL, out_split=rh, **kw)
                 ops.conv([(rh, 128), (x4, 256)], P[f"gru.q{s}"], act=TANH, aux=hf, aux2=z, aux_mode=lib.AUX_GRU,
-                         out_f32=hf.view(1, h, w, 128), out_split=h4, **kw)
+                         out_f32=hf.view(n, h, w, 128), out_split=h4, **kw)
             # flow head (update.py:13-14)
             ops.conv([(h4, 128)], P["fh1"], kx=3, ky=3, pad_x=1, pad_y=1, act=RELU, out_split=fh)
-            ops.conv([(fh, 256)], P["fh2"], kx=3, ky=3, pad_x=1, pad_y=1, act=NONE, out_f32=delta.view(1, h, w, 2))
-            lib.raft_flow_update(coords, delta, h, w, flow_nchw, xbuf, 254)
+            ops.conv([(fh, 256)], P["fh2"], kx=3, ky=3, pad_x=1, pad_y=1, act=NONE, out_f32=delta.view(n, h, w, 2))
+            lib.raft_flow_update(coords, delta, h, w, flow_nchw, xbuf, 254, n=n)
             if not test_mode or it == iters - 1:
                 # mask head scaled by 0.25 (update.py:122-125,135) + convex upsampling (raft.py:73-84)
                 ops.conv([(h4, 128)], P["mask0"], kx=3, ky=3, pad_x=1, pad_y=1, act=RELU, out_split=m0)
-                ops.linear([(m0.view(2, npx, 256), 256)], P["mask2"], npx, alpha=0.25, out_f32=mask)
-                up = torch.empty(2, 8 * h, 8 * w, device=dev)
-                lib.convex_upsample(mask, flow_nchw, h, w, up)
+                ops.linear([(m0.view(2, tot, 256), 256)], P["mask2"], tot, alpha=0.25, out_f32=mask)
+                up = torch.empty(n, 2, 8 * h, 8 * w, device=dev)
+                lib.convex_upsample(mask, flow_nchw, h, w, up, n=n)
                 ups.append(up)
         return flow_nchw.clone(), ups
 
@@ -339,12 +345,7 @@ class RAFT(nn.Module):
         dev = image1.device
         P = self._packed if self._packed is not None else self._pack(dev)
         image1, image2 = image1.float().contiguous(), image2.float().contiguous()
-        lows, ups_all = [], []
-        for i in range(image1.shape[0]):
-            fi = flow_init[i] if flow_init is not None else None
-            lo, ups = self._forward_one(image1[i], image2[i], iters, fi, test_mode, P, dev)
-            lows.append(lo)
-            ups_all.append(ups)
+        lo, ups = self._forward_batch(image1, image2, iters, flow_init, test_mode, P, dev)
         if test_mode:
-            return torch.stack(lows, 0), torch.stack([u[-1] for u in ups_all], 0)
-        return [torch.stack([u[k] for u in ups_all], 0) for k in range(iters)]
+            return lo, ups[-1]
+        return ups

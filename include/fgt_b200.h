@@ -215,13 +215,16 @@ int fgt_corr_lookup(const float* const* level_ptrs_host, const int* level_h_host
                     int levels, int radius, const float* coords, int n_pix, int out_pitch, void* out_hi,
                     long long out_plane, fgt_stream_t stream);
 
-/* coords += delta (delta may be NULL); writes flow = coords - pixel grid as NCHW fp32 [2,h,w] and, if
- * x_hi != NULL, as channels [x_chan, x_chan+1] of the split GRU-input buffer (RAFT/raft.py:127-132). */
-int fgt_raft_flow_update(float* coords, const float* delta, int h, int w, float* flow_nchw, void* x_hi,
+/* coords += delta (delta may be NULL) for n image pairs, coords/delta [n*h*w, 2]; writes
+ * flow = coords - pixel grid as NCHW fp32 [n,2,h,w] and, if x_hi != NULL, as channels
+ * [x_chan, x_chan+1] of the split GRU-input buffer (RAFT/raft.py:127-132). */
+int fgt_raft_flow_update(float* coords, const float* delta, int n, int h, int w, float* flow_nchw, void* x_hi,
                          long long x_plane, int x_pitch, int x_chan, fgt_stream_t stream);
 
-/* RAFT.upsample_flow (RAFT/raft.py:73-84): mask [h*w, 576] fp32 -> up-sampled flow [2, 8h, 8w]. */
-int fgt_convex_upsample(const float* mask, const float* flow_nchw, int h, int w, float* out, fgt_stream_t stream);
+/* RAFT.upsample_flow (RAFT/raft.py:73-84): mask [n*h*w, 576] fp32, flow [n,2,h,w] -> up-sampled flow
+ * [n, 2, 8h, 8w]. */
+int fgt_convex_upsample(const float* mask, const float* flow_nchw, int n, int h, int w, float* out,
+                        fgt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Flow-guided gradient propagation (tool/get_flowNN_gradient.py:11-534, Nonlocal=False). Dense state

@@ -71,6 +71,30 @@ def test_raft_gpu_small(name):
 
 
 @pytest.mark.gpu
+def test_raft_gpu_batch3_vs_oracle_and_single():
+    """n=3 pairs in one call (one GEMM per layer over all pairs) against the oracle on the batch and
+    against three single-pair calls (instance-norm partial sums are split differently, hence 1e-4 rather than
+    bit equality); with a per-pair flow_init."""
+    model, sd = _gpu_model(3)
+    im1, im2 = synth.raft_inputs(seed=13, H=128, W=160, n=3)  # >= 16x16 at 1/8: no 1-pixel pyramid level
+    with torch.no_grad():
+        lo, up = model(im1.cuda(), im2.cuda(), iters=5, test_mode=True)
+        olo, oup = RO.raft_forward(sd, im1, im2, iters=5)
+    assert tuple(lo.shape) == (3, 2, 16, 20) and tuple(up.shape) == (3, 2, 128, 160)
+    assert_close(lo, olo, REL_TOL, "batch low vs oracle")
+    assert_close(up, oup, REL_TOL, "batch up vs oracle")
+    with torch.no_grad():
+        for i in range(3):
+            lo1, up1 = model(im1[i:i + 1].cuda(), im2[i:i + 1].cuda(), iters=5, test_mode=True)
+            assert_close(lo[i:i + 1], lo1, 1e-4, f"batch vs single pair {i}")
+            assert_close(up[i:i + 1], up1, 1e-4, f"batch vs single pair {i} (up)")
+        # warm start: flow_init shifts coords1 only (raft.py:121-122); zero init equals no init
+        z0, zu = model(im1.cuda(), im2.cuda(), iters=2, flow_init=torch.zeros(3, 2, 16, 20).cuda(), test_mode=True)
+        n0, nu = model(im1.cuda(), im2.cuda(), iters=2, test_mode=True)
+    assert torch.equal(zu, nu)
+
+
+@pytest.mark.gpu
 def test_raft_gpu_full_480x864():
     """BASELINE config 3 geometry (the driver feeds RAFT 480x864 for 240x432 clips)."""
     g = load_golden("raft_full_i20")

@@ -78,6 +78,15 @@ with torch.no_grad():
         RO.raft_forward(sd, im1, im2, iters=20)
         r["cpu_oracle_s"] = time.perf_counter() - t0
     res["raft_480x864_i20"] = r
+    # batched + CUDA-graph replay: what a clip driver should call (forward and backward flows of several
+    # frame pairs per call)
+    m.enable_cuda_graph(True)
+    for nb in (1, 4):
+        ib1, ib2 = synth.raft_inputs(seed=5, H=480, W=864, n=nb)
+        ga, gb = ib1.cuda(), ib2.cuda()
+        ms = timed(lambda: m(ga, gb, iters=20, test_mode=True))
+        res[f"raft_480x864_i20_graph_batch{nb}"] = dict(ms_per_call=ms, ms_per_pair=ms / nb, pairs_per_s=1e3 * nb / ms)
+    m.enable_cuda_graph(False)
     # ---- LAFC
     from fgt_b200.lafc_model import Model as LAFC
     from oracle import lafc_oracle as LO
