@@ -92,3 +92,27 @@ def test_fgt_720p_padded_geometry():
         ref = O.fgt_forward(O.strip_net(sd), fr, fl, mk)
     assert tuple(out.shape) == (2, 3, 720, 1280)
     assert_close(out, ref, REL_TOL, "720p T=2")
+
+
+def test_clip_streamer_matches_direct_calls():
+    """fgt_b200.streaming.ClipStreamer (H2D / forward / D2H on three streams, two slots) returns, in order,
+    exactly what direct Model.forward calls return — with and without CUDA-graph replay."""
+    from fgt_b200.fgt_model import Model
+    from fgt_b200.streaming import ClipStreamer
+    cfg = dict(synth.CFG_A)
+    cfg["input_resolution"] = (64, 96)
+    sd = synth.make_state_dict(synth.fgt_param_shapes(cfg), seed=8)
+    model = Model(cfg)
+    model.load_state_dict(sd)
+    model = model.cuda()
+    clips = [[t.contiguous().pin_memory() for t in synth.fgt_inputs(seed=20 + i, t=3, H=64, W=96)] for i in range(5)]
+    with torch.no_grad():
+        direct = [model(*[t.cuda() for t in c]).cpu() for c in clips]
+    for graph in (False, True):
+        model.net.enable_cuda_graph(graph)
+        st = ClipStreamer(model, clips[0])
+        got = [o.clone() for o in st.run(clips)]
+        assert len(got) == 5
+        for i, (a, b) in enumerate(zip(got, direct)):
+            assert torch.equal(a, b), f"clip {i} (graph={graph})"
+    model.net.enable_cuda_graph(False)
