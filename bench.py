@@ -263,9 +263,25 @@ def main():
         assert n_out == args.steps
         return parallel.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps, st
 
+    def timed_frame_sharded():
+        """N>1 only: ONE T=10 window sharded by frames over the ranks (FGT.enable_frame_sharding, NCCL
+        all-gather of the LayerNorm'd zone rows per temporal layer) — strong scaling of a single forward."""
+        mine = parallel.shard_items(T, rank, world)
+        if not mine:
+            return None
+        clip0 = synth.fgt_inputs(seed=3, t=T, H=H, W=W)      # every rank: the same window, its own frames
+        part = [t[:, mine[0]:mine[-1] + 1].contiguous().to(dev) for t in clip0]
+        model.net.enable_frame_sharding(T)
+        try:
+            ms, _ = timed(lambda: model(*part))
+        finally:
+            model.net.enable_frame_sharding(None)
+        return ms
+
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms_dev, launches = timed(step_device)
+    ms_fshard = timed_frame_sharded() if 1 < world <= T else None
     ms_e2e_serial, _ = timed(step_e2e)
     ms_e2e, streamer = timed_streamed()
     clocks = sampler.stop()
@@ -339,6 +355,10 @@ def main():
                            "around all K steps, inputs re-read from host every step",
                     "serial_value": frames / (ms_e2e_serial * 1e-3), "serial_ms_per_step": ms_e2e_serial,
                     "serial_api": "x.to(device) -> Model.forward -> out.cpu(), one stream, per-step events"},
+            "frame_sharded": (None if ms_fshard is None else
+                              {"value": T / (ms_fshard * 1e-3), "unit": "frames/s", "ms_per_step": ms_fshard,
+                               "scaling": "strong", "note": "one T=10 window split by frames over the ranks; NCCL "
+                               "all-gather of LayerNorm'd zone rows per temporal layer; eager launches"}),
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels,
             "cpu_baseline": cpu, "impl": "fgt_b200",
         }))

@@ -440,8 +440,60 @@ class FGT(nn.Module):
         self._linear([lib.ASeg(hid2, hidden, rows)], P[name + ".ffn2"], rows, aux=x, aux_mode=lib.AUX_ADD, out_f32=x,
                      out_split=xs)
 
+    def enable_frame_sharding(self, total_frames, group=None, rank=None, world=None):
+        """Frame-sharded execution of ONE clip window over the ranks of `group`: this rank's
+        forward() then takes only its contiguous frames [1, t_local, ...] (parallel.shard_items(total_frames,
+        rank, world)) and returns their inpainted frames. Everything is per frame except TMHSA, which
+        all-gathers the LayerNorm'd zone rows once per temporal layer. total_frames=None switches it off."""
+        if total_frames is None:
+            self._fshard = None
+            return
+        import torch.distributed as dist
+        from . import parallel
+        if world is None:
+            world = dist.get_world_size(group) if dist.is_initialized() else 1
+            rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._fshard = dict(T=total_frames, group=group, rank=rank, counts=parallel.frame_counts(total_frames, world),
+                            work={})
+
+    def _temporal_sharded(self, g, P, name, x, xs, dev):
+        """TMHSA over all T frames of the window with this rank holding g.t of them: queries = own frames,
+        keys / values = every frame (projected locally from the all-gathered LayerNorm output)."""
+        from . import parallel
+        fs = self._fshard
+        counts = fs["counts"]
+        d, zl = self.d, g.zh * g.zw
+        T, tmax = sum(counts), max(counts)
+        Lzl, Lz, Lqp = g.Lz, T * zl, tmax * zl
+        Lzp = (Lz + 7) // 8 * 8
+        if name + ".q" not in P:
+            w = P[name + ".qk"]
+            P[name + ".q"] = dict(w, w=w["w"][:, :d].contiguous(), b=w["b"][:d].contiguous(), N=d, name=name + ".q")
+            P[name + ".k"] = dict(w, w=w["w"][:, d:].contiguous(), b=w["b"][d:].contiguous(), N=d, name=name + ".k")
+        s_loc = self._buf(g, f"ts_s{T}", (g.zones * Lqp, d), dev, split=True, zero=True)
+        q = self._buf(g, f"ts_q{T}", (g.zones * Lqp, d), dev, split=True)
+        kk = self._buf(g, f"ts_k{T}", (g.zones * Lz, d), dev, split=True)
+        vt = self._buf(g, f"ts_vt{T}", (g.zones, d, Lzp), dev, split=True, zero=True)
+        att = self._buf(g, f"ts_att{T}", (g.zones * Lzl, d), dev, split=True)
+        lib.rownorm(x, None, s_loc, gather=g.zone_map, rows_per_batch=Lzl, total_rows=g.zones * Lzl,
+                    dst_batch_rows=Lqp, eps=LN_EPS, gamma=P[name + ".ln_g"], beta=P[name + ".ln_b"])
+        s_all = parallel.allgather_zone_rows(s_loc.view(2, g.zones, Lqp, d), counts, zl, fs["group"], fs["work"])
+        s_all = s_all.view(2, g.zones * Lz, d)
+        self._linear([lib.ASeg(s_loc, d, g.zones * Lqp)], P[name + ".q"], g.zones * Lqp, out_split=q)
+        self._linear([lib.ASeg(s_all, d, g.zones * Lz)], P[name + ".k"], g.zones * Lz, out_split=kk)
+        self._linear([lib.ASeg(s_all, d, g.zones * Lz)], P[name + ".v"], g.zones * Lz, out_split=vt, lin_batch=Lz,
+                     os_z=d * Lzp, os_x=1, os_c=Lzp)
+        lib.attention(q, kk, vt, att, batches=g.zones, heads=self.heads, Lq=Lzl, Lk=Lz, q_ld=d, k_ld=d, vt_ld=Lzp,
+                      out_ld=d, q_batch_stride=Lqp * d, k_batch_stride=Lz * d, vt_batch_stride=d * Lzp,
+                      out_batch_stride=Lzl * d, scale=1.0 / math.sqrt(d // self.heads), tag=name)
+        self._linear([lib.ASeg(att, d, g.zones * Lzl)], P[name + ".o"], g.zones * Lzl, rowmap=g.zone_map, aux=x,
+                     aux_mode=lib.AUX_ADD, out_f32=x)
+        self._ffn(g, P, name, x, xs, dev)
+
     def _temporal(self, g, P, name, x, xs, dev):
         """TemporalTransformer.forward (model.py:124-130) with TMHSA (attention_base.py:76-106)."""
+        if getattr(self, "_fshard", None) is not None:
+            return self._temporal_sharded(g, P, name, x, xs, dev)
         d, rows_z = self.d, g.zones * g.Lz
         s_zm = self._buf(g, "t_s", (rows_z, d), dev, split=True)
         qk = self._buf(g, "t_qk", (rows_z, 2 * d), dev, split=True)
@@ -508,7 +560,7 @@ class FGT(nn.Module):
     def forward(self, masked_frames, flows, masks):
         if not masked_frames.is_cuda:
             raise RuntimeError("fgt_b200.FGT runs on a CUDA (sm_100a) device only; there is no CPU fallback")
-        if getattr(self, "_graphed", None) is not None and self.capture is None:
+        if getattr(self, "_graphed", None) is not None and self.capture is None and getattr(self, "_fshard", None) is None:
             return self._graphed(masked_frames.float().contiguous(), flows.float().contiguous(),
                                  masks.float().contiguous())
         return self._forward_impl(masked_frames, flows, masks)
@@ -517,6 +569,10 @@ class FGT(nn.Module):
         dev = masked_frames.device
         b, t, c, H, W = masked_frames.shape
         bt = b * t
+        fs = getattr(self, "_fshard", None)
+        if fs is not None and (b != 1 or t != fs["counts"][fs["rank"]]):
+            raise ValueError(f"frame sharding: rank {fs['rank']} expects [1, {fs['counts'][fs['rank']]}, ...] frames "
+                             f"of the {fs['T']}-frame window, got [{b}, {t}, ...]")
         P = self._packed if self._packed is not None else self._pack(dev)
         g = self._geometry(b, t, H, W, dev)
         B = lambda name, shape, **kw: self._buf(g, name, shape, dev, **kw)  # noqa: E731

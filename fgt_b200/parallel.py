@@ -1,9 +1,16 @@
 """Host-side sharding logic for multi-GPU inference.
 
-The driver's FGT stage is a loop over clip windows (tool/video_inpainting.py:710-740): every window
-is an independent Model.forward, so windows shard across ranks with NO data-path collective; the
-only communication is the final gather of the composed frames (or, in bench.py, the MAX-reduce of the
-step time). RAFT pairs and LAFC calls shard the same way (independent per frame pair / per index).
+Two ways to spread the FGT stage over ranks:
+
+* window data parallelism — the driver's loop over clip windows (tool/video_inpainting.py:710-740): every
+  window is an independent Model.forward, so windows shard across ranks with NO data-path collective; the
+  only communication is the final gather of the composed frames (or, in bench.py, the MAX-reduce of the
+  step time). RAFT pairs and LAFC calls shard the same way (independent per frame pair / per index).
+* frame sharding inside one window (`FGT.enable_frame_sharding`) — everything in FGT.forward is per frame
+  except TMHSA, whose (zone, head) attention spans all T frames (attention_base.py:76-106). Each rank keeps
+  its contiguous frames; per temporal layer the LayerNorm'd zone rows are all-gathered (`allgather_zone_rows`,
+  T*n*512*4 B in total), K / V are projected for all frames locally and Q only for the rank's own frames.
+
 `get_flowNN_gradient` is sequential over frames: replicas only.
 """
 import torch
@@ -72,3 +79,50 @@ def gather_frames(local_frames, local_ids, total, device="cpu"):
         dist.all_reduce(acc)
         dist.all_reduce(cnt)
     return acc, cnt
+
+
+def frame_counts(total_frames, world):
+    """Frames per rank for contiguous frame sharding (sizes differ by at most one)."""
+    return [len(shard_items(total_frames, r, world)) for r in range(world)]
+
+
+def allgather_zone_rows(local, counts, rows_per_frame, group=None, work=None):
+    """The exchange step of frame-sharded TMHSA.
+
+    local : [P, Z, tmax*rows_per_frame, d] — this rank's LayerNorm'd tokens in zone-major order (P = 2 bf16
+            planes of the split format, Z zones), frame-major inside a zone and zero-padded to
+            tmax = max(counts) frames so that every rank contributes the same number of bytes.
+    counts: frames owned by each rank (rank order = frame order).
+    Returns [P, Z, sum(counts)*rows_per_frame, d]: every zone's rows of ALL frames in frame order.
+    Rows travel as raw bytes (exact on every backend); with the gloo backend CUDA tensors are staged
+    through the host (used by the single-GPU two-process parity test), with NCCL they stay on the device.
+    """
+    world = len(counts)
+    P, Z, lr, d = local.shape
+    tmax, T = max(counts), sum(counts)
+    assert lr == tmax * rows_per_frame, (lr, tmax, rows_per_frame)
+    key = ("zone_rows", tuple(local.shape), local.dtype, str(local.device), T)
+    if work is not None and key in work:
+        gathered, out = work[key]
+    else:
+        gathered = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+        out = torch.empty((P, Z, T * rows_per_frame, d), dtype=local.dtype, device=local.device)
+        if work is not None:
+            work[key] = (gathered, out)
+    if world == 1:
+        gathered[0].copy_(local)
+    else:
+        as_int = lambda t: t.view(torch.uint8)  # noqa: E731  (raw bytes: exact on every backend)
+        src = as_int(local.contiguous())
+        if dist.get_backend(group) == "gloo" and local.is_cuda:
+            host = [torch.empty(src.shape, dtype=src.dtype) for _ in range(world)]
+            dist.all_gather(host, src.cpu(), group=group)
+            for q in range(world):
+                as_int(gathered[q]).copy_(host[q])
+        else:
+            dist.all_gather_into_tensor(as_int(gathered).view(world * P, Z, lr, -1), src, group=group)
+    off = 0
+    for q, cnt in enumerate(counts):
+        out[:, :, off * rows_per_frame:(off + cnt) * rows_per_frame].copy_(gathered[q][:, :, :cnt * rows_per_frame])
+        off += cnt
+    return out

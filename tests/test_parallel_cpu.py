@@ -86,3 +86,45 @@ def test_gloo_world2_gather_and_max():
         assert all(abs(a - c * i) < 1e-6 for i, (a, c) in enumerate(zip(acc0, cnt)))  # sum over covering windows
         assert mx == pytest.approx(11.0)                  # MAX over ranks of (10 + rank)
     assert sorted(res[0][1] + res[1][1]) == list(range(len(sched)))
+
+
+def _zone_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        T, Z, rpf, d = 5, 4, 6, 8                       # 5 frames over 2 ranks: 3 + 2 (uneven -> padding path)
+        counts = parallel.frame_counts(T, world)
+        full = torch.arange(2 * Z * T * rpf * d, dtype=torch.float32).reshape(2, Z, T * rpf, d).to(torch.bfloat16)
+        mine = parallel.shard_items(T, rank, world)
+        local = torch.zeros(2, Z, max(counts) * rpf, d, dtype=torch.bfloat16)
+        local[:, :, :len(mine) * rpf] = full[:, :, mine[0] * rpf:(mine[-1] + 1) * rpf]
+        work = {}
+        out = parallel.allgather_zone_rows(local, counts, rpf, None, work)
+        out2 = parallel.allgather_zone_rows(local, counts, rpf, None, work)   # cached workspace path
+        q.put((rank, counts, bool(torch.equal(out, full)), bool(torch.equal(out2, full)), len(work)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_allgather_zone_rows():
+    """The exchange step of frame-sharded TMHSA: every rank ends up with all frames' zone rows in frame
+    order, bit-exact, also when the frame counts are uneven (3 + 2)."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_zone_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, counts, ok, ok2, nwork in res:
+        assert counts == [3, 2] and ok and ok2 and nwork == 1
+
+
+def test_allgather_zone_rows_world1_is_identity():
+    x = torch.randn(2, 3, 8, 4).to(torch.bfloat16)
+    assert torch.equal(parallel.allgather_zone_rows(x, [2], 4), x)
