@@ -31,6 +31,7 @@ sys.path.insert(0, ROOT)
 from fgt_b200 import synth  # noqa: E402
 
 T, H, W = 10, 240, 432
+RESULT_OUT = sys.stdout
 METRIC = "inpainted_frames_per_sec_432x240_T10"
 WORKLOAD = "FGT full inference (Model.forward), synthetic 432x240 clip T=10, random mask, seeded random weights"
 
@@ -175,7 +176,7 @@ def run_reference(args, rank, world):
                          "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    }), file=RESULT_OUT, flush=True)
 
 
 def main():
@@ -189,6 +190,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries exactly one JSON line: anything native libraries print to fd 1 (e.g. NCCL's version banner)
+    # is sent to stderr, and the result line goes to the saved descriptor
+    global RESULT_OUT
+    sys.stdout.flush()
+    RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -362,7 +369,7 @@ def main():
                                "all-gather of LayerNorm'd zone rows per temporal layer; eager launches"}),
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels,
             "cpu_baseline": cpu, "impl": "fgt_b200",
-        }))
+        }), file=RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
