@@ -120,12 +120,20 @@ __global__ void im2col_nchw_kernel(const float* __restrict__ s0, int c0, const f
 // One warp per destination row; two-pass mean / variance in registers.
 // ------------------------------------------------------------------------------------------
 constexpr int kNormMaxVec = 8;  // up to 8 float4 per lane -> C <= 1024
+constexpr int kNormMaxDst = 8;  // destinations of one normalised row: the local buffer and/or NVLink peers
+
+// Destination buffers of the normalised rows. More than one = the exchange step of frame-sharded TMHSA
+// fused into the LayerNorm: every rank stores its rows straight into all peers' K/V-input buffers
+// (P2P stores over NVLink), so no separate all-gather and no re-ordering copy is needed.
+struct NormDests {
+  __nv_bfloat16* hi[kNormMaxDst];
+  int n;
+};
 
 __global__ void rownorm_kernel(const float* __restrict__ a, int ca, int lda, const float* __restrict__ b, int cb,
                                int ldb, const int* __restrict__ gather, int rows_per_batch, long long total_rows,
                                int dst_batch_rows, int dst_row0, const float* __restrict__ gamma,
-                               const float* __restrict__ beta, __nv_bfloat16* __restrict__ hi, long long plane,
-                               float eps) {
+                               const float* __restrict__ beta, const NormDests dst, long long plane, float eps) {
   const int C = ca + cb;
   const int lane = threadIdx.x & 31;
   const long long warp_id = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
@@ -134,14 +142,15 @@ __global__ void rownorm_kernel(const float* __restrict__ a, int ca, int lda, con
   for (long long d = warp_id; d < total_rows; d += nwarps) {
     const long long bidx = d / rows_per_batch;
     const long long drow = bidx * dst_batch_rows + dst_row0 + (d - bidx * rows_per_batch);
-    __nv_bfloat16* oh = hi + drow * C;
-    __nv_bfloat16* ol = oh + plane;
+    const long long ooff = drow * C;
     long long src = d;
     if (gather) src = gather[d];
     if (src < 0) {
-      for (int v = lane; v < nvec; v += 32) {
-        *reinterpret_cast<uint2*>(oh + v * 4) = make_uint2(0u, 0u);
-        *reinterpret_cast<uint2*>(ol + v * 4) = make_uint2(0u, 0u);
+      for (int q = 0; q < dst.n; ++q) {
+        for (int v = lane; v < nvec; v += 32) {
+          *reinterpret_cast<uint2*>(dst.hi[q] + ooff + v * 4) = make_uint2(0u, 0u);
+          *reinterpret_cast<uint2*>(dst.hi[q] + ooff + plane + v * 4) = make_uint2(0u, 0u);
+        }
       }
       continue;
     }
@@ -178,7 +187,13 @@ __global__ void rownorm_kernel(const float* __restrict__ a, int ca, int lda, con
           const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + v * 4));
           o.x = o.x * gm.x + bt.x; o.y = o.y * gm.y + bt.y; o.z = o.z * gm.z + bt.z; o.w = o.w * gm.w + bt.w;
         }
-        store_split4(oh + v * 4, ol + v * 4, o.x, o.y, o.z, o.w);
+        uint32_t h0, l0, h1, l1;
+        split_bf16x2(o.x, o.y, h0, l0);
+        split_bf16x2(o.z, o.w, h1, l1);
+        for (int q = 0; q < dst.n; ++q) {
+          *reinterpret_cast<uint2*>(dst.hi[q] + ooff + v * 4) = make_uint2(h0, h1);
+          *reinterpret_cast<uint2*>(dst.hi[q] + ooff + plane + v * 4) = make_uint2(l0, l1);
+        }
       }
     }
   }
@@ -396,15 +411,30 @@ extern "C" int fgt_rownorm(const float* a, int ca, int lda, const float* b, int 
                            int rows_per_batch, long long total_rows, int dst_batch_rows, int dst_row0,
                            const float* gamma, const float* beta, void* out_hi, long long out_plane, float eps,
                            fgt_stream_t stream) {
+  void* one[1] = {out_hi};
+  return fgt_rownorm_bcast(a, ca, lda, b, cb, ldb, gather, rows_per_batch, total_rows, dst_batch_rows, dst_row0,
+                           gamma, beta, one, 1, out_plane, eps, stream);
+}
+
+extern "C" int fgt_rownorm_bcast(const float* a, int ca, int lda, const float* b, int cb, int ldb, const int* gather,
+                                 int rows_per_batch, long long total_rows, int dst_batch_rows, int dst_row0,
+                                 const float* gamma, const float* beta, void* const* out_his_host, int n_out,
+                                 long long out_plane, float eps, fgt_stream_t stream) {
   const int C = ca + cb;
+  FGT_REQUIRE(out_his_host && n_out >= 1 && n_out <= kNormMaxDst, FGT_ERR_ARG, "rownorm: n_out=%d", n_out);
+  NormDests dst;
+  for (int q = 0; q < kNormMaxDst; ++q)
+    dst.hi[q] = q < n_out ? reinterpret_cast<__nv_bfloat16*>(out_his_host[q]) : nullptr;
+  dst.n = n_out;
+  for (int q = 0; q < n_out; ++q) FGT_REQUIRE(dst.hi[q], FGT_ERR_ARG, "rownorm: destination %d is NULL", q);
   FGT_REQUIRE(a && ca % 4 == 0 && cb % 4 == 0 && C <= 128 * kNormMaxVec && lda % 4 == 0 && (cb == 0 || (b && ldb % 4 == 0)),
               FGT_ERR_ARG, "rownorm: ca=%d cb=%d lda=%d ldb=%d", ca, cb, lda, ldb);
   FGT_REQUIRE(rows_per_batch >= 1 && total_rows >= 1, FGT_ERR_ARG, "rownorm: rows");
   FGT_REQUIRE((gamma == nullptr) == (beta == nullptr), FGT_ERR_ARG, "rownorm: gamma and beta go together");
   const int block = 256;
   rownorm_kernel<<<grid_for(total_rows * 32, block), block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      a, ca, lda, b, cb, ldb, gather, rows_per_batch, total_rows, dst_batch_rows, dst_row0, gamma, beta,
-      reinterpret_cast<__nv_bfloat16*>(out_hi), out_plane, eps);
+      a, ca, lda, b, cb, ldb, gather, rows_per_batch, total_rows, dst_batch_rows, dst_row0, gamma, beta, dst,
+      out_plane, eps);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;
 }

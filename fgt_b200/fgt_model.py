@@ -440,27 +440,87 @@ class FGT(nn.Module):
         self._linear([lib.ASeg(hid2, hidden, rows)], P[name + ".ffn2"], rows, aux=x, aux_mode=lib.AUX_ADD, out_f32=x,
                      out_split=xs)
 
-    def enable_frame_sharding(self, total_frames, group=None, rank=None, world=None):
+    def enable_frame_sharding(self, total_frames, group=None, rank=None, world=None, exchange="p2p"):
         """Frame-sharded execution of ONE clip window over the ranks of `group`: this rank's
         forward() then takes only its contiguous frames [1, t_local, ...] (parallel.shard_items(total_frames,
-        rank, world)) and returns their inpainted frames. Everything is per frame except TMHSA, which
-        all-gathers the LayerNorm'd zone rows once per temporal layer. total_frames=None switches it off."""
+        rank, world)) and returns their inpainted frames. Everything is per frame except TMHSA, which needs
+        the LayerNorm'd zone rows of all frames once per temporal layer:
+          exchange="p2p"  — the LayerNorm kernel stores its rows straight into every peer's K/V-input buffer
+                            over NVLink (fgt_rownorm_bcast) and a device-side barrier orders them
+                            (fgt_peer_barrier); no collective call, CUDA-graph replayable;
+          exchange="nccl" — torch.distributed all-gather of the rows + re-ordering copies (the baseline).
+        total_frames=None switches sharding off. Collective: every rank of the group must call it."""
         if total_frames is None:
             self._fshard = None
             return
         import torch.distributed as dist
         from . import parallel
+        if exchange not in ("p2p", "nccl"):
+            raise ValueError(f"exchange={exchange!r}")
         if world is None:
             world = dist.get_world_size(group) if dist.is_initialized() else 1
             rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._fshard = dict(T=total_frames, group=group, rank=rank, counts=parallel.frame_counts(total_frames, world),
-                            work={})
+                            work={}, exchange=exchange, layer=0)
+        if exchange == "p2p":
+            if getattr(self, "_peer", None) is None:
+                from .peer import PeerGroup
+                self._peer = PeerGroup(group, rank, world)
+            self._fshard["peer"] = self._peer
+
+    def _temporal_sharded_p2p(self, g, P, name, x, xs, dev):
+        """Frame-sharded TMHSA with the exchange fused into the LayerNorm: rows go to all peers by P2P stores."""
+        fs = self._fshard
+        counts, rank, pg = fs["counts"], fs["rank"], fs["peer"]
+        d, zl = self.d, g.zh * g.zw
+        T, off = sum(counts), sum(counts[:rank])
+        Lzl, Lz = g.Lz, T * zl
+        Lzp = (Lz + 7) // 8 * 8
+        plane = g.zones * Lz * d
+        key = ("s_all", g.zones, Lz, d)
+        if key not in fs["work"]:
+            bufs = []
+            for _ in range(2):  # double-buffered by layer parity: a peer may still read layer i while i+1 is written
+                ptrs, view = pg.alloc(2 * plane * 2)
+                bufs.append((ptrs, view.view(torch.bfloat16).view(2, g.zones * Lz, d)))
+            fs["work"][key] = bufs
+        ptrs, s_all = fs["work"][key][fs["layer"] % 2]
+        fs["layer"] += 1
+        if name + ".q" not in P:
+            w = P[name + ".qk"]
+            P[name + ".q"] = dict(w, w=w["w"][:, :d].contiguous(), b=w["b"][:d].contiguous(), N=d, name=name + ".q")
+            P[name + ".k"] = dict(w, w=w["w"][:, d:].contiguous(), b=w["b"][d:].contiguous(), N=d, name=name + ".k")
+        q = self._buf(g, f"tp_q{T}", (g.zones * Lzl, d), dev, split=True)
+        kk = self._buf(g, f"tp_k{T}", (g.zones * Lz, d), dev, split=True)
+        vt = self._buf(g, f"tp_vt{T}", (g.zones, d, Lzp), dev, split=True, zero=True)
+        att = self._buf(g, f"tp_att{T}", (g.zones * Lzl, d), dev, split=True)
+        lib.rownorm_bcast(x, ptrs, plane, gather=g.zone_map, rows_per_batch=Lzl, total_rows=g.zones * Lzl,
+                          dst_batch_rows=Lz, dst_row0=off * zl, eps=LN_EPS, gamma=P[name + ".ln_g"],
+                          beta=P[name + ".ln_b"])
+        pg.barrier()
+        # Q only for this rank's frames: rows [off*zl, off*zl + Lzl) of every zone, read in place (strided view)
+        wq = P[name + ".q"]
+        bw, bh = _pick_box(Lzl, g.zones)
+        lib.gemm_tc([lib.ASeg(s_all, d, Lzl, g.zones, 1, sx=d, sy=Lz * d, elem_offset=off * zl * d)], wq["w"], d,
+                    out_w=Lzl, out_h=g.zones, box_w=bw, box_h=bh, bn=_pick_bn(d, 1, wq["name"]), bias=wq["b"],
+                    out_split=q, os_x=d, os_y=Lzl * d, tag=wq["name"])
+        self._linear([lib.ASeg(s_all, d, g.zones * Lz)], P[name + ".k"], g.zones * Lz, out_split=kk)
+        self._linear([lib.ASeg(s_all, d, g.zones * Lz)], P[name + ".v"], g.zones * Lz, out_split=vt, lin_batch=Lz,
+                     os_z=d * Lzp, os_x=1, os_c=Lzp)
+        lib.attention(q, kk, vt, att, batches=g.zones, heads=self.heads, Lq=Lzl, Lk=Lz, q_ld=d, k_ld=d, vt_ld=Lzp,
+                      out_ld=d, q_batch_stride=Lzl * d, k_batch_stride=Lz * d, vt_batch_stride=d * Lzp,
+                      out_batch_stride=Lzl * d, scale=1.0 / math.sqrt(d // self.heads), tag=name)
+        self._linear([lib.ASeg(att, d, g.zones * Lzl)], P[name + ".o"], g.zones * Lzl, rowmap=g.zone_map, aux=x,
+                     aux_mode=lib.AUX_ADD, out_f32=x)
+        self._ffn(g, P, name, x, xs, dev)
 
     def _temporal_sharded(self, g, P, name, x, xs, dev):
         """TMHSA over all T frames of the window with this rank holding g.t of them: queries = own frames,
         keys / values = every frame (projected locally from the all-gathered LayerNorm output)."""
         from . import parallel
         fs = self._fshard
+        if fs["exchange"] == "p2p":
+            return self._temporal_sharded_p2p(g, P, name, x, xs, dev)
         counts = fs["counts"]
         d, zl = self.d, g.zh * g.zw
         T, tmax = sum(counts), max(counts)
@@ -560,7 +620,9 @@ class FGT(nn.Module):
     def forward(self, masked_frames, flows, masks):
         if not masked_frames.is_cuda:
             raise RuntimeError("fgt_b200.FGT runs on a CUDA (sm_100a) device only; there is no CPU fallback")
-        if getattr(self, "_graphed", None) is not None and self.capture is None and getattr(self, "_fshard", None) is None:
+        fs = getattr(self, "_fshard", None)
+        graph_ok = fs is None or fs["exchange"] == "p2p"  # NCCL calls are not captured; the P2P exchange is kernels only
+        if getattr(self, "_graphed", None) is not None and self.capture is None and graph_ok:
             return self._graphed(masked_frames.float().contiguous(), flows.float().contiguous(),
                                  masks.float().contiguous())
         return self._forward_impl(masked_frames, flows, masks)
@@ -573,6 +635,9 @@ class FGT(nn.Module):
         if fs is not None and (b != 1 or t != fs["counts"][fs["rank"]]):
             raise ValueError(f"frame sharding: rank {fs['rank']} expects [1, {fs['counts'][fs['rank']]}, ...] frames "
                              f"of the {fs['T']}-frame window, got [{b}, {t}, ...]")
+        if fs is not None and fs["exchange"] == "p2p":
+            fs["layer"] = 0
+            fs["peer"].barrier()  # every peer has finished reading the exchange buffers of the previous forward
         P = self._packed if self._packed is not None else self._pack(dev)
         g = self._geometry(b, t, H, W, dev)
         B = lambda name, shape, **kw: self._buf(g, name, shape, dev, **kw)  # noqa: E731

@@ -76,6 +76,17 @@ def load():
     lib.fgt_im2col_nchw.argtypes = [_c_p, ci, _c_p, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, cf, cf, _c_p, cll, _c_p]
     lib.fgt_im2col_nchw.restype = ctypes.c_int
     lib.fgt_rownorm.argtypes = [_c_p, ci, ci, _c_p, ci, ci, _c_p, ci, cll, ci, ci, _c_p, _c_p, _c_p, cll, cf, _c_p]
+    lib.fgt_rownorm_bcast.argtypes = [_c_p, ci, ci, _c_p, ci, ci, _c_p, ci, cll, ci, ci, _c_p, _c_p, _c_p, ci, cll, cf, _c_p]
+    lib.fgt_rownorm_bcast.restype = ctypes.c_int
+    lib.fgt_peer_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]
+    lib.fgt_peer_free.argtypes = [_c_p]
+    lib.fgt_peer_export.argtypes = [_c_p, ctypes.c_char_p]
+    lib.fgt_peer_import.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]
+    lib.fgt_peer_unimport.argtypes = [_c_p]
+    lib.fgt_peer_barrier.argtypes = [_c_p, ci, ci, _c_p, _c_p]
+    for fn in (lib.fgt_peer_alloc, lib.fgt_peer_free, lib.fgt_peer_export, lib.fgt_peer_import, lib.fgt_peer_unimport,
+               lib.fgt_peer_barrier):
+        fn.restype = ctypes.c_int
     lib.fgt_dwpool.argtypes = [_c_p, ci, _c_p, ci, ci, ci, ci, ci, ci, ci, _c_p, _c_p, _c_p, _c_p]
     lib.fgt_dwconv3x3_res.argtypes = [_c_p, ci, ci, ci, ci, _c_p, _c_p, _c_p, _c_p, cll, _c_p]
     lib.fgt_fold.argtypes = [_c_p, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, _c_p, _c_p, _c_p, cll, _c_p]
@@ -110,6 +121,13 @@ def check(rc, what):
         msg = load().fgt_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"{what} failed (code {rc}): {msg}")
     COUNTERS["launches"] += 1
+
+
+def check_rc(rc, what):
+    """check() for calls that launch no kernel (allocation, IPC)."""
+    if rc != 0:
+        msg = load().fgt_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
 
 
 # Kernel-launch counter (bench.py's "gpu_launches") and optional per-launch CUDA-event profiler.
@@ -304,6 +322,18 @@ def rownorm(a, b, out_split, *, gather=None, rows_per_batch, total_rows, dst_bat
         check(load().fgt_rownorm(_dp(a), ca, lda, _dp(b), cb, ldb, _dp(gather), rows_per_batch, total_rows,
                                  dst_batch_rows, dst_row0, _dp(gamma), _dp(beta), _dp(out_split),
                                  plane_elems(out_split), eps, stream_ptr()), "fgt_rownorm")
+
+
+def rownorm_bcast(a, dst_ptrs, plane, *, gather=None, rows_per_batch, total_rows, dst_batch_rows, dst_row0=0, eps=1e-5,
+                  gamma=None, beta=None, tag=""):
+    """LayerNorm rows of `a` stored to every buffer in dst_ptrs (raw device addresses of split-bf16 buffers with
+    the lo plane `plane` elements after the hi plane; local or peer-mapped)."""
+    ca = a.shape[-1]
+    arr = (_c_p * len(dst_ptrs))(*dst_ptrs)
+    with _Prof("rownorm", tag, 0, 4.0 * total_rows * ca * (1 + len(dst_ptrs))):
+        check(load().fgt_rownorm_bcast(_dp(a), ca, ca, None, 0, 0, _dp(gather), rows_per_batch, total_rows,
+                                       dst_batch_rows, dst_row0, _dp(gamma), _dp(beta), arr, len(dst_ptrs), plane, eps,
+                                       stream_ptr()), "fgt_rownorm_bcast")
 
 
 def dwpool(a, b, bt, h, w, k, gh, gw, weight, bias, out, tag=""):

@@ -166,6 +166,32 @@ int fgt_rownorm(const float* a, int ca, int lda, const float* b, int cb, int ldb
                 int rows_per_batch, long long total_rows, int dst_batch_rows, int dst_row0, const float* gamma,
                 const float* beta, void* out_hi, long long out_plane, float eps, fgt_stream_t stream);
 
+/* Same, with the normalised rows stored to n_out (<= 8) destination buffers of identical layout
+ * (out_his_host: HOST array of device pointers, local or peer-mapped). With the peers' K/V-input
+ * buffers as destinations this is LayerNorm fused with the all-gather of frame-sharded TMHSA
+ * (attention_base.py:84-98 across ranks): P2P stores over NVLink, followed by fgt_peer_barrier. */
+int fgt_rownorm_bcast(const float* a, int ca, int lda, const float* b, int cb, int ldb, const int* gather,
+                      int rows_per_batch, long long total_rows, int dst_batch_rows, int dst_row0, const float* gamma,
+                      const float* beta, void* const* out_his_host, int n_out, long long out_plane, float eps,
+                      fgt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Peer memory for the multi-GPU exchange (no reference counterpart: the reference's inference is
+ * single-device). One process per GPU; buffers are cudaMalloc'ed here (IPC-capable,
+ * zero-initialised), exported as 64-byte CUDA IPC handles that the host side exchanges over its
+ * process group, and imported by the peers (peer access enabled lazily).
+ * fgt_peer_barrier: device-side barrier among n ranks on `stream` — flags_host[q] is (a mapping of)
+ * rank q's flag array of n uint64 (zero-initialised); epoch_ctr is a local device uint64 that the
+ * kernel increments, so the call is CUDA-graph replayable. Release/acquire at system scope: all
+ * peer stores issued by earlier kernels on `stream` are visible to the peers' kernels that follow
+ * their barrier. Spins at most ~10 s, then traps (a lost rank must not hang the GPU). */
+int fgt_peer_alloc(size_t bytes, void** ptr);
+int fgt_peer_free(void* ptr);
+int fgt_peer_export(void* ptr, unsigned char handle[64]);
+int fgt_peer_import(const unsigned char handle[64], void** ptr);
+int fgt_peer_unimport(void* ptr);
+int fgt_peer_barrier(void* const* flags_host, int n, int rank, void* epoch_ctr, fgt_stream_t stream);
+
 /* Depthwise k x k, stride k convolution (+bias) of the token grid [bt,h,w,ca+cb], zero-padded to
  * (gh*k, gw*k) -> fp32 [bt, gh*gw, ca+cb]. weight is the torch layout [C,1,k,k].
  * Replaces global_extract_k / global_extract_v, attention_flow.py:135,145. */

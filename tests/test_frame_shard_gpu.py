@@ -2,8 +2,11 @@
 
 Two processes share cuda:0 and talk over gloo (NCCL refuses two ranks on one device; the helper stages
 the all-gather through the host for gloo), so the full sharded code path — Q for own frames, K/V for all
-frames from the all-gathered LayerNorm rows, uneven 3+2 split — runs on the single-GPU test box. With
-two or more GPUs the same test also runs over NCCL, one rank per device."""
+frames from the all-gathered LayerNorm rows, uneven 3+2 split — runs on the single-GPU test box, for both
+exchanges: the torch.distributed all-gather and the fused P2P one (LayerNorm storing into the peers'
+buffers through CUDA IPC mappings + the device-side barrier; two processes on one GPU are time-sliced, so
+the barrier's spin simply waits for the other process's slice). With two or more GPUs the same test also
+runs over NCCL / NVLink, one rank per device."""
 import os
 import socket
 
@@ -44,14 +47,23 @@ def _worker(rank, world, port, backend, q):
         with torch.no_grad():
             full = model(fr, fl, mk)                                  # unsharded reference on every rank
             mine = parallel.shard_items(T, rank, world)
-            model.net.enable_frame_sharding(T)
             sl = slice(mine[0], mine[-1] + 1)
-            part = model(fr[:, sl], fl[:, sl], mk[:, sl])
-            part2 = model(fr[:, sl], fl[:, sl], mk[:, sl])            # cached workspaces / second call
+            errs, same = {}, True
+            for exchange in ("nccl", "p2p"):   # "nccl" = torch.distributed all-gather (gloo here when backend is gloo)
+                model.net.enable_frame_sharding(T, exchange=exchange)
+                part = model(fr[:, sl], fl[:, sl], mk[:, sl])
+                part2 = model(fr[:, sl], fl[:, sl], mk[:, sl])        # cached workspaces / second call
+                errs[exchange] = (part - full[sl]).abs().max().item() / full.abs().max().item()
+                same = same and bool(torch.equal(part, part2))
+            # the P2P exchange is kernels only -> the whole sharded forward replays as a CUDA graph
+            model.net.enable_cuda_graph(True)
+            for _ in range(3):
+                gpart = model(fr[:, sl], fl[:, sl], mk[:, sl])
+            same = same and bool(torch.equal(gpart, part))
+            model.net.enable_cuda_graph(False)
             model.net.enable_frame_sharding(None)
             again = model(fr, fl, mk)
-        err = (part - full[sl]).abs().max().item() / full.abs().max().item()
-        q.put((rank, mine, tuple(part.shape), err, bool(torch.equal(part, part2)), bool(torch.equal(again, full))))
+        q.put((rank, mine, tuple(part.shape), errs, same, bool(torch.equal(again, full))))
     finally:
         dist.destroy_process_group()
 
@@ -72,8 +84,9 @@ def test_frame_sharded_forward_matches_unsharded(backend):
         p.join(timeout=120)
         assert p.exitcode == 0
     assert [r[1] for r in res] == [[0, 1, 2], [3, 4]]
-    for rank, mine, shape, err, same, restored in res:
+    for rank, mine, shape, errs, same, restored in res:
         assert shape == (len(mine), 3, H, W)
         # same kernels and the same per-row arithmetic; only tile boundaries of the split problem differ
-        assert err < 1e-5, f"rank {rank}: sharded vs unsharded max/max = {err:.3e}"
+        for exchange, err in errs.items():
+            assert err < 1e-5, f"rank {rank} ({exchange}): sharded vs unsharded max/max = {err:.3e}"
         assert same and restored
