@@ -291,7 +291,15 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms_dev, launches = timed(step_device)
-    ms_fshard = timed_frame_sharded() if 1 < world <= T else None
+    # measured on 2 GPUs this round; larger groups only on request (an untested group size must not be able to
+    # take the headline measurement down with it)
+    want_fs = world == 2 or (1 < world <= T and os.environ.get("FGT_BENCH_FRAME_SHARD") == "1")
+    ms_fshard = None
+    if want_fs:
+        try:
+            ms_fshard = timed_frame_sharded()
+        except Exception as exc:  # noqa: BLE001 - reported, never fatal for the main line
+            print(f"[bench] frame-sharded measurement failed: {exc}", file=sys.stderr)
     ms_e2e_serial, _ = timed(step_e2e)
     ms_e2e, streamer = timed_streamed()
     clocks = sampler.stop()
