@@ -282,24 +282,17 @@ def main():
         out = {}
         for exchange in ("nccl", "p2p"):
             model.net.enable_frame_sharding(T, exchange=exchange)
+            model.net.enable_cuda_graph(exchange == "p2p")   # kernels only -> replayable; NCCL calls stay eager
             try:
                 out[exchange], _ = timed(lambda: model(*part))
             finally:
+                model.net.enable_cuda_graph(False)
                 model.net.enable_frame_sharding(None)
         return out
 
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms_dev, launches = timed(step_device)
-    # measured on 2 GPUs this round; larger groups only on request (an untested group size must not be able to
-    # take the headline measurement down with it)
-    want_fs = world == 2 or (1 < world <= T and os.environ.get("FGT_BENCH_FRAME_SHARD") == "1")
-    ms_fshard = None
-    if want_fs:
-        try:
-            ms_fshard = timed_frame_sharded()
-        except Exception as exc:  # noqa: BLE001 - reported, never fatal for the main line
-            print(f"[bench] frame-sharded measurement failed: {exc}", file=sys.stderr)
     ms_e2e_serial, _ = timed(step_e2e)
     ms_e2e, streamer = timed_streamed()
     clocks = sampler.stop()
@@ -354,6 +347,15 @@ def main():
         cpu = {"value": fps_cpu, "unit": "frames/s", "cores": threads, "host_cores": os.cpu_count(), "kind": "port",
                "sample": f"1 warm-up + 2 forwards of the same T=10 432x240 clip ({sec:.2f} s each), oracle/fgt_oracle.py"}
 
+    # measured on 2 GPUs this round; larger groups only on request (an untested group size must not be able to
+    # take the headline measurement down with it)
+    want_fs = world == 2 or (1 < world <= T and os.environ.get("FGT_BENCH_FRAME_SHARD") == "1")
+    ms_fshard = None
+    if want_fs:
+        try:
+            ms_fshard = timed_frame_sharded()
+        except Exception as exc:  # noqa: BLE001 - reported, never fatal for the main line
+            print(f"[bench] frame-sharded measurement failed: {exc}", file=sys.stderr)
     if rank == 0:
         frames = T * world
         h2d = sum(t.numel() * t.element_size() for t in host)
