@@ -1,5 +1,7 @@
 // Error plumbing, device probing and TMA descriptor encoding (driver entry point fetched at run time,
 // so the library links against the CUDA runtime only and loads on hosts without a driver).
+#include <stdlib.h>
+
 #include "common.h"
 
 #include <cudaTypedefs.h>
@@ -70,6 +72,15 @@ int encode_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t
                    (unsigned long long)(rank > 4 ? gdim[4] : 0), bx[0], rank > 1 ? bx[1] : 0, rank > 2 ? bx[2] : 0,
                    rank > 3 ? bx[3] : 0, rank > 4 ? bx[4] : 0);
   return FGT_OK;
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("FGT_PDL");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on == 1;
 }
 
 int num_sms() {

@@ -99,6 +99,9 @@ __global__ void __launch_bounds__(256, 1) flash_kernel(const __grid_constant__ F
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // PDL: the prologue above overlapped the previous kernel's tail; nothing before this line touches global data
+  pdl_launch_dependents();
+  pdl_wait();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -429,7 +432,7 @@ int attention_launch(const FgtAttnDesc& d, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid((d.Lq + 127) / 128, d.heads, d.batches);
-  flash_kernel<<<grid, 256, kFlashSmem, stream>>>(p);
+  launch_k(flash_kernel, dim3(grid), dim3(256), kFlashSmem, stream, p);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;
 }

@@ -238,6 +238,9 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem_base) : "r"(tmem_slot));
+  // PDL: the prologue above overlapped the previous kernel's tail; nothing before this line touches global data
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int tiles_per_z = p.tiles_x * p.tiles_y;
 
@@ -550,8 +553,8 @@ int gemm_tc_launch(const FgtGemmDesc& d, cudaStream_t stream) {
   int grid = num_sms();
   if (grid > p.total_tiles) grid = p.total_tiles;
   FGT_REQUIRE(grid >= 1, FGT_ERR_ARG, "gemm_tc: empty problem");
-  if (ext) gemm_tc_kernel<1><<<grid, 192, smem, stream>>>(p);
-  else gemm_tc_kernel<0><<<grid, 192, smem, stream>>>(p);
+  if (ext) launch_k(gemm_tc_kernel<1>, dim3(grid), dim3(192), smem, stream, p);
+  else launch_k(gemm_tc_kernel<0>, dim3(grid), dim3(192), smem, stream, p);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;
 }

@@ -26,6 +26,8 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // no reset is ever needed. The epoch lives in device memory and is advanced here, which keeps the launch
 // identical from call to call (CUDA-graph replay).
 __global__ void peer_barrier_kernel(const PeerFlags pf, unsigned long long* __restrict__ epoch_ctr) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ unsigned long long epoch_s;
   if (threadIdx.x == 0) {
     epoch_s = *epoch_ctr + 1ull;
@@ -102,7 +104,7 @@ extern "C" int fgt_peer_barrier(void* const* flags_host, int n, int rank, void* 
   pf.n = n;
   pf.rank = rank;
   for (int q = 0; q < n; ++q) FGT_REQUIRE(pf.flags[q], FGT_ERR_ARG, "peer_barrier: flags[%d] is NULL", q);
-  peer_barrier_kernel<<<1, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(peer_barrier_kernel, dim3(1), dim3(32), 0, reinterpret_cast<cudaStream_t>(stream), 
       pf, reinterpret_cast<unsigned long long*>(epoch_ctr));
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;

@@ -42,6 +42,8 @@ __global__ void prop_step_kernel(const uint8_t* __restrict__ mask, const float* 
                                  const float* __restrict__ back, int H, int W, int t, int tn, double thres,
                                  double* __restrict__ nn_y, double* __restrict__ nn_x, int* __restrict__ nn_t,
                                  uint8_t* __restrict__ have, double* __restrict__ cuv) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int HW = H * W;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
     if (!mask[static_cast<long long>(t) * HW + p]) continue;
@@ -87,6 +89,8 @@ __global__ void prop_step_kernel(const uint8_t* __restrict__ mask, const float* 
 __global__ void prop_gather_kernel(const uint8_t* __restrict__ mask, const double* __restrict__ nn_y,
                                    const double* __restrict__ nn_x, const int* __restrict__ nn_t, int N, int H,
                                    int W, int s, float* __restrict__ gx, float* __restrict__ gy) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long HW = static_cast<long long>(H) * W;
   const long long total = HW * N;
   const float* sx = gx + s * HW * 3;
@@ -110,6 +114,8 @@ __global__ void prop_fuse_kernel(const uint8_t* __restrict__ mask, const uint8_t
                                  const float* __restrict__ gxb, const float* __restrict__ gyb,
                                  const float* __restrict__ gxf, const float* __restrict__ gyf,
                                  float* __restrict__ gx, float* __restrict__ gy, uint8_t* __restrict__ tofill) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long o = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; o < total;
        o += static_cast<long long>(gridDim.x) * blockDim.x) {
     const bool m = mask[o] != 0;
@@ -152,7 +158,7 @@ extern "C" int fgt_prop_step(const uint8_t* mask, const float* flow_step, const 
                              int tn, double thres, double* nn_y, double* nn_x, int* nn_t, uint8_t* have, double* cuv,
                              fgt_stream_t stream) {
   FGT_REQUIRE(mask && flow_step && flow_back && nn_y && nn_x && nn_t && have && cuv, FGT_ERR_ARG, "prop_step: null");
-  prop_step_kernel<<<grid1(static_cast<long long>(H) * W, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(prop_step_kernel, dim3(grid1(static_cast<long long>(H) * W, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       mask, flow_step, flow_back, H, W, t, tn, thres, nn_y, nn_x, nn_t, have, cuv);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;
@@ -161,7 +167,7 @@ extern "C" int fgt_prop_step(const uint8_t* mask, const float* flow_step, const 
 extern "C" int fgt_prop_gather(const uint8_t* mask, const double* nn_y, const double* nn_x, const int* nn_t, int N,
                                int H, int W, int s, float* gx, float* gy, fgt_stream_t stream) {
   FGT_REQUIRE(mask && nn_y && nn_x && nn_t && gx && gy, FGT_ERR_ARG, "prop_gather: null");
-  prop_gather_kernel<<<grid1(static_cast<long long>(N) * H * W, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(prop_gather_kernel, dim3(grid1(static_cast<long long>(N) * H * W, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       mask, nn_y, nn_x, nn_t, N, H, W, s, gx, gy);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;
@@ -173,7 +179,7 @@ extern "C" int fgt_prop_fuse(const uint8_t* mask, const uint8_t* have0, const ui
                              uint8_t* tofill, fgt_stream_t stream) {
   FGT_REQUIRE(mask && have0 && have1 && cuv0 && cuv1 && gx && gy && tofill, FGT_ERR_ARG, "prop_fuse: null");
   const long long total = static_cast<long long>(N) * H * W;
-  prop_fuse_kernel<<<grid1(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(prop_fuse_kernel, dim3(grid1(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       mask, have0, have1, cuv0, cuv1, total, alpha, gx_bn, gy_bn, gx_fn, gy_fn, gx, gy, tofill);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;

@@ -23,6 +23,8 @@ static int grid_cap(long long work_items, int block) {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512) chan_stats_kernel(const float* __restrict__ x, int HW, int C,
                                                          int rows_per_block, double* __restrict__ stats) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red_s[512], red_q[512];
   const int img = blockIdx.y;
   const int r0 = blockIdx.x * rows_per_block;
@@ -69,6 +71,8 @@ __global__ void __launch_bounds__(512) chan_stats_kernel(const float* __restrict
 __global__ void instnorm_act_kernel(const float* __restrict__ x, const double* __restrict__ stats, int HW, int C,
                                     float eps, int relu, const float* __restrict__ res, float* __restrict__ out,
                                     __nv_bfloat16* __restrict__ hi, long long plane) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sc[256], sh[256];
   const int img = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -115,6 +119,8 @@ __global__ void instnorm_act_kernel(const float* __restrict__ x, const double* _
 // 2x2 average pooling of the last two dims of [rows, h, w] (F.avg_pool2d(corr, 2, stride=2), corr.py:25-27)
 // ------------------------------------------------------------------------------------------
 __global__ void avgpool2_kernel(const float* __restrict__ in, long long rows, int h, int w, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int oh = h / 2, ow = w / 2;
   const long long total = rows * oh * ow;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -142,6 +148,8 @@ struct LookupLevels {
 
 __global__ void corr_lookup_kernel(LookupLevels lv, int levels, int radius, const float* __restrict__ coords,
                                    int n_pix, int out_pitch, __nv_bfloat16* __restrict__ hi, long long plane) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float patch_smem[];
   const int warps_per_block = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -189,6 +197,8 @@ __global__ void corr_lookup_kernel(LookupLevels lv, int levels, int radius, cons
 __global__ void flow_update_kernel(float* __restrict__ coords, const float* __restrict__ delta, int n_img, int h,
                                    int w, float* __restrict__ flow_nchw, __nv_bfloat16* __restrict__ x_hi,
                                    long long x_plane, int x_pitch, int x_chan) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = h * w;
   for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_img * n; p += gridDim.x * blockDim.x) {
     const int img = p / n, q = p - img * n;
@@ -220,6 +230,8 @@ __global__ void flow_update_kernel(float* __restrict__ coords, const float* __re
 // ------------------------------------------------------------------------------------------
 __global__ void convex_upsample_kernel(const float* __restrict__ mask, const float* __restrict__ flow_all, int n_img,
                                        int h, int w, float* __restrict__ out_all) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = h * w;
   const long long total = static_cast<long long>(n_img) * n * 64;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -270,7 +282,7 @@ extern "C" int fgt_chan_stats(const float* x, int n, int HW, int C, double* stat
   rows_per_block = ((rows_per_block + rstep - 1) / rstep) * rstep;
   if (rows_per_block < 8 * rstep) rows_per_block = 8 * rstep;
   dim3 grid((HW + rows_per_block - 1) / rows_per_block, n);
-  chan_stats_kernel<<<grid, 512, 0, st>>>(x, HW, C, rows_per_block, stats);
+  launch_k(chan_stats_kernel, dim3(grid), dim3(512), 0, st, x, HW, C, rows_per_block, stats);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;
 }
@@ -282,7 +294,7 @@ extern "C" int fgt_instnorm_act(const float* x, const double* stats, int n, int 
   FGT_REQUIRE(C <= 256, FGT_ERR_ARG, "instnorm_act: C=%d > 256", C);
   const long long total = static_cast<long long>(HW) * (C / 4);
   const dim3 grid(grid_cap(total, 256), n);
-  instnorm_act_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(instnorm_act_kernel, dim3(grid), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       x, stats, HW, C, eps, relu, res, out, reinterpret_cast<__nv_bfloat16*>(out_hi), out_plane);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;
@@ -291,7 +303,7 @@ extern "C" int fgt_instnorm_act(const float* x, const double* stats, int n, int 
 extern "C" int fgt_avgpool2(const float* in, long long rows, int h, int w, float* out, fgt_stream_t stream) {
   FGT_REQUIRE(in && out && h >= 2 && w >= 2, FGT_ERR_ARG, "avgpool2: %dx%d", h, w);
   const long long total = rows * (h / 2) * (w / 2);
-  avgpool2_kernel<<<grid_cap(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(in, rows, h, w, out);
+  launch_k(avgpool2_kernel, dim3(grid_cap(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), in, rows, h, w, out);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;
 }
@@ -312,7 +324,7 @@ extern "C" int fgt_corr_lookup(const float* const* level_ptrs_host, const int* l
   const int block = 256;
   const size_t smem = (block / 32) * (win + 1) * (win + 1) * sizeof(float);
   const long long items = static_cast<long long>(n_pix) * levels;
-  corr_lookup_kernel<<<grid_cap(items * 32, block), block, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(corr_lookup_kernel, dim3(grid_cap(items * 32, block)), dim3(block), smem, reinterpret_cast<cudaStream_t>(stream), 
       lv, levels, radius, coords, n_pix, out_pitch, reinterpret_cast<__nv_bfloat16*>(out_hi), out_plane);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;
@@ -321,8 +333,7 @@ extern "C" int fgt_corr_lookup(const float* const* level_ptrs_host, const int* l
 extern "C" int fgt_raft_flow_update(float* coords, const float* delta, int n, int h, int w, float* flow_nchw,
                                     void* x_hi, long long x_plane, int x_pitch, int x_chan, fgt_stream_t stream) {
   FGT_REQUIRE(coords && flow_nchw && n >= 1, FGT_ERR_ARG, "raft_flow_update: null argument");
-  flow_update_kernel<<<grid_cap(static_cast<long long>(n) * h * w, 256), 256, 0,
-                       reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(flow_update_kernel, dim3(grid_cap(static_cast<long long>(n) * h * w, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       coords, delta, n, h, w, flow_nchw, reinterpret_cast<__nv_bfloat16*>(x_hi), x_plane, x_pitch, x_chan);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;
@@ -332,7 +343,7 @@ extern "C" int fgt_convex_upsample(const float* mask, const float* flow_nchw, in
                                    fgt_stream_t stream) {
   FGT_REQUIRE(mask && flow_nchw && out && n >= 1, FGT_ERR_ARG, "convex_upsample: null argument");
   const long long total = static_cast<long long>(n) * h * w * 64;
-  convex_upsample_kernel<<<grid_cap(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(convex_upsample_kernel, dim3(grid_cap(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       mask, flow_nchw, n, h, w, out);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;

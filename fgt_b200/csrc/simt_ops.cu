@@ -29,6 +29,8 @@ __device__ __forceinline__ void store_split4(__nv_bfloat16* hi, __nv_bfloat16* l
 // ------------------------------------------------------------------------------------------
 __global__ void pack_nchw_kernel(const float* __restrict__ s0, int c0, const float* __restrict__ s1, int c1, int n,
                                  int H, int W, int pad, int cpad, __nv_bfloat16* __restrict__ hi, long long plane) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int Wp = W + 2 * pad, Hp = H + 2 * pad;
   const long long total = static_cast<long long>(n) * Hp * Wp;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -59,6 +61,8 @@ __global__ void im2col_nchw_kernel(const float* __restrict__ s0, int c0, const f
                                    int n, int H, int W, int k, int stride, int pad, int replicate, int OH, int OW,
                                    int cpad, float scale, float shift, __nv_bfloat16* __restrict__ hi,
                                    long long plane) {
+  pdl_launch_dependents();
+  pdl_wait();
   // one block = one output row (b, oy); threadIdx.x = 8-channel group, threadIdx.y strides over ox.
   // The channel -> (source channel, dy, dx) decode is a per-block shared-memory table: no per-element
   // integer divisions in the loop (they dominated the first version of this kernel).
@@ -134,6 +138,8 @@ __global__ void rownorm_kernel(const float* __restrict__ a, int ca, int lda, con
                                int ldb, const int* __restrict__ gather, int rows_per_batch, long long total_rows,
                                int dst_batch_rows, int dst_row0, const float* __restrict__ gamma,
                                const float* __restrict__ beta, const NormDests dst, long long plane, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int C = ca + cb;
   const int lane = threadIdx.x & 31;
   const long long warp_id = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
@@ -207,6 +213,8 @@ __global__ void rownorm_kernel(const float* __restrict__ a, int ca, int lda, con
 __global__ void dwpool_kernel(const float* __restrict__ a, int ca, const float* __restrict__ b, int cb, int bt,
                               int h, int w, int k, int gh, int gw, const float* __restrict__ wt,
                               const float* __restrict__ bias, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int C = ca + cb;
   const long long total = static_cast<long long>(bt) * gh * gw * C;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -238,6 +246,8 @@ __global__ void dwpool_kernel(const float* __restrict__ a, int ca, const float* 
 __global__ void dwconv3_res_kernel(const float* __restrict__ x, int bt, int h, int w, int C,
                                    const float* __restrict__ wt, const float* __restrict__ bias,
                                    float* __restrict__ out, __nv_bfloat16* __restrict__ hi, long long plane) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = static_cast<long long>(bt) * h * w * C;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -280,6 +290,8 @@ __global__ void dwconv3_res_kernel(const float* __restrict__ x, int bt, int h, i
 __global__ void fold_kernel(const float* __restrict__ hid, int bt, int th, int tw, int C, int kh, int kw, int st,
                             int pd, int OH, int OW, int normalize, const float* __restrict__ add,
                             float* __restrict__ out, __nv_bfloat16* __restrict__ hi, long long plane) {
+  pdl_launch_dependents();
+  pdl_wait();
   // one block = one output row (b, y); threadIdx.x = float4 channel group, threadIdx.y strides over x.
   // The contributing token rows are block-uniform; no per-element integer divisions by runtime values.
   const int C4 = C / 4;
@@ -322,6 +334,8 @@ __global__ void fold_kernel(const float* __restrict__ hid, int bt, int th, int t
 // One block = one token; threadIdx.x = float4 channel group, threadIdx.y strides over the kh*kw positions.
 __global__ void unfold_kernel(const float* __restrict__ img, int bt, int th, int tw, int C, int kh, int kw, int st,
                               int pd, int OH, int OW, int relu, __nv_bfloat16* __restrict__ hi, long long plane) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int C4 = C / 4;
   if (threadIdx.x >= C4) return;
   const int P = kh * kw;
@@ -351,6 +365,8 @@ __global__ void unfold_kernel(const float* __restrict__ img, int bt, int th, int
 // nearest x2 upsampling of an NHWC split tensor (F.interpolate(scale_factor=2), network_blocks_2d.py:58-60)
 __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ in, long long in_plane, int n, int H, int W,
                                   int C, __nv_bfloat16* __restrict__ out, long long out_plane) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int C8 = C / 8;
   const long long total = 2LL * n * (2 * H) * (2 * W) * C8;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -386,7 +402,7 @@ extern "C" int fgt_pack_nchw(const float* src0, int c0, const float* src1, int c
   FGT_REQUIRE(src0 && c0 >= 1 && c0 + c1 <= cpad && cpad % 8 == 0 && (c1 == 0 || src1), FGT_ERR_ARG,
               "pack_nchw: c0=%d c1=%d cpad=%d", c0, c1, cpad);
   const long long total = static_cast<long long>(n) * (H + 2 * pad) * (W + 2 * pad);
-  pack_nchw_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(pack_nchw_kernel, dim3(grid_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       src0, c0, src1, c1, n, H, W, pad, cpad, reinterpret_cast<__nv_bfloat16*>(out_hi), out_plane);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;
@@ -400,7 +416,7 @@ extern "C" int fgt_im2col_nchw(const float* src0, int c0, const float* src1, int
               FGT_ERR_ARG, "im2col_nchw: k=%d cin=%d cpad=%d", k, c0 + c1, cpad);
   FGT_REQUIRE(cpad <= 256, FGT_ERR_ARG, "im2col_nchw: cpad=%d > 256", cpad);
   const dim3 blk(cpad / 8, 256 / (cpad / 8));
-  im2col_nchw_kernel<<<n * OH, blk, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(im2col_nchw_kernel, dim3(n * OH), dim3(blk), 0, reinterpret_cast<cudaStream_t>(stream), 
       src0, c0, src1, c1, n, H, W, k, stride, pad, replicate, OH, OW, cpad, scale, shift,
       reinterpret_cast<__nv_bfloat16*>(out_hi), out_plane);
   FGT_CUDA(cudaGetLastError());
@@ -432,7 +448,7 @@ extern "C" int fgt_rownorm_bcast(const float* a, int ca, int lda, const float* b
   FGT_REQUIRE(rows_per_batch >= 1 && total_rows >= 1, FGT_ERR_ARG, "rownorm: rows");
   FGT_REQUIRE((gamma == nullptr) == (beta == nullptr), FGT_ERR_ARG, "rownorm: gamma and beta go together");
   const int block = 256;
-  rownorm_kernel<<<grid_for(total_rows * 32, block), block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(rownorm_kernel, dim3(grid_for(total_rows * 32, block)), dim3(block), 0, reinterpret_cast<cudaStream_t>(stream), 
       a, ca, lda, b, cb, ldb, gather, rows_per_batch, total_rows, dst_batch_rows, dst_row0, gamma, beta, dst,
       out_plane, eps);
   FGT_CUDA(cudaGetLastError());
@@ -443,7 +459,7 @@ extern "C" int fgt_dwpool(const float* a, int ca, const float* b, int cb, int bt
                           int gw, const float* weight, const float* bias, float* out, fgt_stream_t stream) {
   FGT_REQUIRE(a && weight && bias && out && k >= 1 && gh >= 1 && gw >= 1, FGT_ERR_ARG, "dwpool: bad argument");
   const long long total = static_cast<long long>(bt) * gh * gw * (ca + cb);
-  dwpool_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a, ca, b, cb, bt, h, w, k,
+  launch_k(dwpool_kernel, dim3(grid_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), a, ca, b, cb, bt, h, w, k,
                                                                                         gh, gw, weight, bias, out);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;
@@ -453,7 +469,7 @@ extern "C" int fgt_dwconv3x3_res(const float* x, int bt, int h, int w, int C, co
                                  float* out, void* out_hi, long long out_plane, fgt_stream_t stream) {
   FGT_REQUIRE(x && weight && bias && out, FGT_ERR_ARG, "dwconv3x3_res: null argument");
   const long long total = static_cast<long long>(bt) * h * w * C;
-  dwconv3_res_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(dwconv3_res_kernel, dim3(grid_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       x, bt, h, w, C, weight, bias, out, reinterpret_cast<__nv_bfloat16*>(out_hi), out_plane);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;
@@ -466,7 +482,7 @@ extern "C" int fgt_fold(const float* hid, int bt, int th, int tw, int C, int kh,
   FGT_REQUIRE(C / 4 <= 64, FGT_ERR_ARG, "fold: C=%d > 256", C);
   const int gx = (C / 4 + 1) / 2 * 2;  // channel groups per row of the thread block
   const dim3 blk(gx, 256 / gx);
-  fold_kernel<<<bt * OH, blk, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(fold_kernel, dim3(bt * OH), dim3(blk), 0, reinterpret_cast<cudaStream_t>(stream), 
       hid, bt, th, tw, C, kh, kw, stride, pad, OH, OW, normalize, add, out, reinterpret_cast<__nv_bfloat16*>(out_hi),
       out_plane);
   FGT_CUDA(cudaGetLastError());
@@ -479,7 +495,7 @@ extern "C" int fgt_unfold(const float* img, int bt, int th, int tw, int C, int k
   FGT_REQUIRE(C / 4 <= 64, FGT_ERR_ARG, "unfold: C=%d > 256", C);
   const int gx = (C / 4 + 1) / 2 * 2;
   const dim3 blk(gx, 256 / gx);
-  unfold_kernel<<<bt * th * tw, blk, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(unfold_kernel, dim3(bt * th * tw), dim3(blk), 0, reinterpret_cast<cudaStream_t>(stream), 
       img, bt, th, tw, C, kh, kw, stride, pad, OH, OW, relu, reinterpret_cast<__nv_bfloat16*>(out_hi), out_plane);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;
@@ -489,7 +505,7 @@ extern "C" int fgt_upsample2x(const void* in_hi, long long in_plane, int n, int 
                               long long out_plane, fgt_stream_t stream) {
   FGT_REQUIRE(in_hi && out_hi && C % 8 == 0, FGT_ERR_ARG, "upsample2x: C=%d", C);
   const long long total = 2LL * n * (2 * H) * (2 * W) * (C / 8);
-  upsample2x_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  launch_k(upsample2x_kernel, dim3(grid_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(in_hi), in_plane, n, H, W, C, reinterpret_cast<__nv_bfloat16*>(out_hi),
       out_plane);
   FGT_CUDA(cudaGetLastError());
