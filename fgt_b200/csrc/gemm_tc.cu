@@ -120,6 +120,31 @@ __device__ __forceinline__ void epi_chunk(const EpiArgs& e, const uint32_t (&raw
 #pragma unroll
     for (int j = 0; j < NC; ++j) v[j] = tanhf(v[j]);
   }
+  if (kExt && e.aux_mode == FGT_AUX_GRU_ZR) {  // fused z | r gates: two C-channel outputs (host guarantees vec)
+    const int half = e.N >> 1;
+    if (col0 < half) {
+      float4* op = reinterpret_cast<float4*>(e.out_f32 + off + col0);
+#pragma unroll
+      for (int q = 0; q < NC / 4; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    } else {
+      const long long o = off + (col0 - half);
+      const float4* ap = reinterpret_cast<const float4*>(e.aux + o);
+      uint4* hp = reinterpret_cast<uint4*>(e.out_hi + o);
+      uint4* lp = reinterpret_cast<uint4*>(e.out_hi + e.out_plane + o);
+#pragma unroll
+      for (int q = 0; q < NC / 8; ++q) {
+        const float4 a0 = __ldg(ap + 2 * q), a1 = __ldg(ap + 2 * q + 1);
+        uint32_t hw[4], lw[4];
+        split_bf16x2(v[8 * q] * a0.x, v[8 * q + 1] * a0.y, hw[0], lw[0]);
+        split_bf16x2(v[8 * q + 2] * a0.z, v[8 * q + 3] * a0.w, hw[1], lw[1]);
+        split_bf16x2(v[8 * q + 4] * a1.x, v[8 * q + 5] * a1.y, hw[2], lw[2]);
+        split_bf16x2(v[8 * q + 6] * a1.z, v[8 * q + 7] * a1.w, hw[3], lw[3]);
+        hp[q] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        lp[q] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      }
+    }
+    return;
+  }
   if (vec) {
     const long long o = off + col0;
     if (e.aux_mode == FGT_AUX_ADD) {
@@ -549,7 +574,11 @@ int gemm_tc_launch(const FgtGemmDesc& d, cudaStream_t stream) {
     attr_set = true;
   }
   const bool ext = d.aux_mode == FGT_AUX_ADD_PRE || d.aux_mode == FGT_AUX_ADD_RELU || d.aux_mode == FGT_AUX_GRU ||
-                   d.act == FGT_ACT_LEAKY001;
+                   d.aux_mode == FGT_AUX_GRU_ZR || d.act == FGT_ACT_LEAKY001;
+  if (d.aux_mode == FGT_AUX_GRU_ZR)
+    FGT_REQUIRE(d.out_f32 && d.out_hi && p.vec_ok && d.N % 64 == 0 && (d.N / 2) % d.bn == 0 && d.groups == 1, FGT_ERR_ARG,
+                "gemm_tc: FGT_AUX_GRU_ZR needs both outputs, aligned unit-stride channels, N=%d a multiple of 64 and "
+                "bn=%d dividing N/2", d.N, d.bn);
   int grid = num_sms();
   if (grid > p.total_tiles) grid = p.total_tiles;
   FGT_REQUIRE(grid >= 1, FGT_ERR_ARG, "gemm_tc: empty problem");

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfgt_sm100a.so")
 
 ACT_NONE, ACT_LEAKY02, ACT_RELU, ACT_SIGMOID, ACT_TANH, ACT_LEAKY001 = 0, 1, 2, 3, 4, 5
-AUX_NONE, AUX_ADD, AUX_MUL, AUX_ADD_PRE, AUX_ADD_RELU, AUX_GRU = 0, 1, 2, 3, 4, 5
+AUX_NONE, AUX_ADD, AUX_MUL, AUX_ADD_PRE, AUX_ADD_RELU, AUX_GRU, AUX_GRU_ZR = 0, 1, 2, 3, 4, 5, 6
 
 _c_ll = ctypes.c_longlong
 _c_p = ctypes.c_void_p

@@ -145,9 +145,10 @@ class RAFT(nn.Module):
         put("convf1", u + "encoder.convf1", im2col=128)
         put("convf2", u + "encoder.convf2")
         put("mconv", u + "encoder.conv")
-        for g in "zrq":
-            for s in "12":
-                put(f"gru.{g}{s}", u + f"gru.conv{g}{s}", segs=[128, 256])
+        for s in "12":
+            put(f"gru.q{s}", u + f"gru.convq{s}", segs=[128, 256])
+            (wz, bz), (wr, br) = wb(u + f"gru.convz{s}", None), wb(u + f"gru.convr{s}", None)
+            P[f"gru.zr{s}"] = ops.packed(f"gru.zr{s}", torch.cat([wz, wr], 0), torch.cat([bz, br], 0), dev, [128, 256])
         put("fh1", u + "flow_head.conv1")
         put("fh2", u + "flow_head.conv2")
         put("mask0", u + "mask.0")
@@ -307,8 +308,9 @@ class RAFT(nn.Module):
             # SepConvGRU (update.py:45-60): horizontal (1x5) then vertical (5x1)
             for s, (kx, ky) in (("1", (5, 1)), ("2", (1, 5))):
                 kw = dict(kx=kx, ky=ky, pad_x=kx // 2, pad_y=ky // 2, seg_counts=[128, 256])
-                ops.conv([(h4, 128), (x4, 256)], P[f"gru.z{s}"], act=SIG, out_f32=z.view(n, h, w, 128), **kw)
-                ops.conv([(h4, 128), (x4, 256)], P[f"gru.r{s}"], act=SIG, aux=hf, aux_mode=lib.AUX_MUL, out_split=rh, **kw)
+                # z = sigmoid(convz(hx)) and r*h = sigmoid(convr(hx)) * h as ONE N=256 GEMM over the shared input
+                ops.conv([(h4, 128), (x4, 256)], P[f"gru.zr{s}"], act=SIG, aux=hf, aux_mode=lib.AUX_GRU_ZR,
+                         out_f32=z.view(n, h, w, 128), out_split=rh, out_c_total=128, **kw)
                 ops.conv([(rh, 128), (x4, 256)], P[f"gru.q{s}"], act=TANH, aux=hf, aux2=z, aux_mode=lib.AUX_GRU,
                          out_f32=hf.view(n, h, w, 128), out_split=h4, **kw)
             # flow head (update.py:13-14)

@@ -45,9 +45,12 @@ enum {
 enum { FGT_ACT_NONE = 0, FGT_ACT_LEAKY02 = 1, FGT_ACT_RELU = 2, FGT_ACT_SIGMOID = 3, FGT_ACT_TANH = 4,
        FGT_ACT_LEAKY001 = 5 /* nn.LeakyReLU() default slope, LAFC/models/lafc.py:138 */ };
 /* aux: out = act(v) + aux | act(v) * aux | act(v + aux) | relu(act(v) + aux) |
- *      (1 - aux2) * aux + aux2 * act(v)   (the ConvGRU state update, RAFT/update.py:52,58) */
+ *      (1 - aux2) * aux + aux2 * act(v)   (the ConvGRU state update, RAFT/update.py:52,58) |
+ *      GRU_ZR: the z and r gate convolutions of a ConvGRU as ONE GEMM with N = 2*C (update.py:48-49,54-55):
+ *      columns [0,C) -> out_f32 = act(v) (z), columns [C,2C) -> out_hi = act(v) * aux (r*h); both outputs
+ *      and aux have C channels per position (output strides describe a C-channel buffer). */
 enum { FGT_AUX_NONE = 0, FGT_AUX_ADD = 1, FGT_AUX_MUL = 2, FGT_AUX_ADD_PRE = 3, FGT_AUX_ADD_RELU = 4,
-       FGT_AUX_GRU = 5 };
+       FGT_AUX_GRU = 5, FGT_AUX_GRU_ZR = 6 };
 
 int fgt_version(void);
 const char* fgt_last_error(void);
