@@ -209,7 +209,8 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     model, sd = build_model(dev)
-    model.net.enable_cuda_graph(True)  # public option: whole forward replayed as one CUDA graph per geometry
+    use_graph = os.environ.get("FGT_BENCH_GRAPH", "1") != "0"   # 0: eager launches (fixed kernel count per step, for ncu)
+    model.net.enable_cuda_graph(use_graph)  # public option: whole forward replayed as one CUDA graph per geometry
     clip = synth.fgt_inputs(seed=3 + rank, t=T, H=H, W=W)
     host = [t.contiguous().pin_memory() for t in clip]
     devin = [t.to(dev) for t in host]
@@ -366,7 +367,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3 (split-bf16 operands, fp32 accumulate)",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": T, "parallelism": f"window-dp{world}",
-                       "cuda_graph": True,
+                       "cuda_graph": use_graph,
                        "l2": "256 MiB buffer rewritten between steps (untimed); activations (>1 GB) exceed L2"},
             "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,

@@ -42,8 +42,9 @@ if os.path.exists(lp):
     tot = sum(a[1] for a in agg.values())
     with open(os.path.join(PR, f"{tag}_launches.md"), "w") as fh:
         fh.write(f"# ncu launch list, one bench.py step ({len(rows)} launches of fgt:: kernels, {tot:.0f} us serialised)\n\n")
-        fh.write("command: `ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled "
-                 "-k regex:fgt:: -s 375 -c 125 --csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline`\n\n")
+        fh.write("command: `FGT_BENCH_GRAPH=0 ncu --metrics gpu__time_duration.sum --clock-control none "
+                 "--kernel-name-base demangled -k regex:fgt:: -s 402 -c 134 --csv python bench.py --steps 2 --warmup 3 "
+                 "--no-cpu-baseline` (eager launches so that one step = 134 launches; skip = 3 warm-up steps)\n\n")
         fh.write("Per-launch times under ncu are cold-cache and serialised: compare SHARES with bench.py's "
                  "`kernels` block, not absolutes.\n\n| kernel | launches | us | share |\n|---|---:|---:|---:|\n")
         for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
