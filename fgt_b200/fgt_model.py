@@ -318,6 +318,9 @@ class FGT(nn.Module):
         conv("dec2", "decoder.layer2.featureConv")
         deconv("dec3", "decoder.layer3.conv.featureConv")
         conv("dec4", "decoder.final.featureConv")
+        # final 64->3 conv as "taps as N": a 1x1 GEMM with N = 9*3 (padded to 32) + fgt_tapsum (shift, add, bias, tanh)
+        w4 = sd["decoder.final.featureConv.weight"]
+        put("dec4t", lib.pack_taps_as_n(w4), torch.zeros(32))
         self._packed = P
         return P
 
@@ -722,7 +725,9 @@ class FGT(nn.Module):
         self._deconv(feat, c2, bt, OH, OW, P, "dec1", d1)
         self._conv(d1, c2, bt, H2, W2, P["dec2"], 3, out_split=d2)
         self._deconv(d2, c2 // 2, bt, H2, W2, P, "dec3", d3)
-        self._conv(d3, c2 // 2, bt, H, W, P["dec4"], 3, act=lib.ACT_TANH, out_f32=out, nchw_out=True)
+        y4 = B("dec4_y", (32, bt * H * W))  # column-planar partial products
+        self._linear([lib.ASeg(d3, c2 // 2, bt * H * W)], P["dec4t"], bt * H * W, out_f32=y4, os_x=1, os_c=bt * H * W)
+        lib.tapsum(y4, bt, H, W, 3, 3, P["dec4"]["b"], lib.ACT_TANH, out, nchw=True, tag="dec4")
         return out
 
 

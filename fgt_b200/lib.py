@@ -87,6 +87,8 @@ def load():
     for fn in (lib.fgt_peer_alloc, lib.fgt_peer_free, lib.fgt_peer_export, lib.fgt_peer_import, lib.fgt_peer_unimport,
                lib.fgt_peer_barrier):
         fn.restype = ctypes.c_int
+    lib.fgt_tapsum.argtypes = [_c_p, ci, ci, ci, ci, ci, ci, ci, ci, cll, _c_p, ci, _c_p, cll, cll, cll, cll, _c_p]
+    lib.fgt_tapsum.restype = ctypes.c_int
     lib.fgt_dwpool.argtypes = [_c_p, ci, _c_p, ci, ci, ci, ci, ci, ci, ci, _c_p, _c_p, _c_p, _c_p]
     lib.fgt_dwconv3x3_res.argtypes = [_c_p, ci, ci, ci, ci, _c_p, _c_p, _c_p, _c_p, cll, _c_p]
     lib.fgt_fold.argtypes = [_c_p, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, _c_p, _c_p, _c_p, cll, _c_p]
@@ -334,6 +336,26 @@ def rownorm_bcast(a, dst_ptrs, plane, *, gather=None, rows_per_batch, total_rows
         check(load().fgt_rownorm_bcast(_dp(a), ca, ca, None, 0, 0, _dp(gather), rows_per_batch, total_rows,
                                        dst_batch_rows, dst_row0, _dp(gamma), _dp(beta), arr, len(dst_ptrs), plane, eps,
                                        stream_ptr()), "fgt_rownorm_bcast")
+
+
+def tapsum(y, n, H, W, cout, k, bias, act, out, *, nchw, tag=""):
+    """out = act(bias + sum over the k*k taps of the shifted columns of the column-planar y [cols, n*H*W]);
+    out is [n,cout,H,W] (nchw) or [n,H,W,cout] fp32. The producing GEMM stores with os_x=1, os_c=n*H*W."""
+    ycol = y.shape[-1]
+    st = (cout * H * W, W, 1, H * W) if nchw else (H * W * cout, W * cout, cout, 1)
+    with _Prof("tapsum", tag, 0, 4.0 * n * H * W * (k * k * cout + cout)):
+        check(load().fgt_tapsum(_dp(y), n, H, W, cout, k, k, k // 2, k // 2, ycol, _dp(bias), act, _dp(out), *st,
+                                stream_ptr()), "fgt_tapsum")
+
+
+def pack_taps_as_n(w, n_pad=32):
+    """[cout, cin, k, k] conv weight -> [n_pad, cin, 1, 1] weight of the equivalent 1x1 'taps as N' GEMM
+    (row tap*cout + c = W[c, :, ty, tx]; zero rows up to n_pad so that the epilogue takes the vector path)."""
+    cout, cin, ky, kx = w.shape
+    assert ky * kx * cout <= n_pad
+    t = torch.zeros(n_pad, cin, 1, 1, dtype=w.dtype, device=w.device)
+    t[:ky * kx * cout, :, 0, 0] = w.permute(2, 3, 0, 1).reshape(ky * kx * cout, cin)
+    return t
 
 
 def dwpool(a, b, bt, h, w, k, gh, gw, weight, bias, out, tag=""):

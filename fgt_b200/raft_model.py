@@ -151,6 +151,8 @@ class RAFT(nn.Module):
             P[f"gru.zr{s}"] = ops.packed(f"gru.zr{s}", torch.cat([wz, wr], 0), torch.cat([bz, br], 0), dev, [128, 256])
         put("fh1", u + "flow_head.conv1")
         put("fh2", u + "flow_head.conv2")
+        w2 = sd[u + "flow_head.conv2.weight"]
+        P["fh2t"] = ops.packed("fh2t", lib.pack_taps_as_n(w2), torch.zeros(32), dev)
         put("mask0", u + "mask.0")
         put("mask2", u + "mask.2")
         P["mask2"]["b"] = P["mask2"]["b"] * 0.25  # mask = 0.25 * conv(x) (update.py:135): alpha scales W x
@@ -288,6 +290,7 @@ class RAFT(nn.Module):
         rh = B("rh", (n, h, w, 128))
         fh = B("fh", (n, h, w, 256))
         delta = B("delta", (tot, 2), split=False)
+        fh2y = B("fh2y", (32, tot), split=False)  # column-planar partial products of the flow head
         m0 = B("m0", (n, h, w, 256))
         mask = B("mask", (tot, 576), split=False)
         h4 = hsp.view(2, n, h, w, 128)
@@ -315,7 +318,9 @@ class RAFT(nn.Module):
                          out_f32=hf.view(n, h, w, 128), out_split=h4, **kw)
             # flow head (update.py:13-14)
             ops.conv([(h4, 128)], P["fh1"], kx=3, ky=3, pad_x=1, pad_y=1, act=RELU, out_split=fh)
-            ops.conv([(fh, 256)], P["fh2"], kx=3, ky=3, pad_x=1, pad_y=1, act=NONE, out_f32=delta.view(n, h, w, 2))
+            # 256->2 conv as "taps as N" (1x1 GEMM with N = 18 -> 32, then shift-and-add): A is read once, not 9x
+            ops.linear([(fh.view(2, tot, 256), 256)], P["fh2t"], tot, out_f32=fh2y, os_x=1, os_c=tot)
+            lib.tapsum(fh2y, n, h, w, 2, 3, P["fh2"]["b"], NONE, delta, nchw=False, tag="fh2")
             lib.raft_flow_update(coords, delta, h, w, flow_nchw, xbuf, 254, n=n)
             if not test_mode or it == iters - 1:
                 # mask head scaled by 0.25 (update.py:122-125,135) + convex upsampling (raft.py:73-84)

@@ -195,6 +195,16 @@ int fgt_peer_import(const unsigned char handle[64], void** ptr);
 int fgt_peer_unimport(void* ptr);
 int fgt_peer_barrier(void* const* flags_host, int n, int rank, void* epoch_ctr, fgt_stream_t stream);
 
+/* Second half of a k x k convolution with <= 4 output channels computed "taps as N": y is column-planar
+ * fp32, y[(tap*cout + c) * ycol + p] = <W[c,:,tap], in[p,:]> for every INPUT pixel p of [n,H,W] (one 1x1
+ * fgt_gemm_tc launch with os_x = 1, os_c = ycol: A read once instead of once per tap); this kernel forms
+ * out[n,y,x,c] = act(bias[c] + sum_tap y[(tap*cout + c) * ycol + (n, y+ty-pad_y, x+tx-pad_x)]) with zero padding and
+ * arbitrary output strides (NCHW or NHWC). Replaces the output side of nn.Conv2d(64, 3, 3) + tanh at
+ * FGT/models/model.py:185-193 and of FlowHead.conv2 at RAFT/update.py:10-14. */
+int fgt_tapsum(const float* y, int n, int H, int W, int cout, int kx, int ky, int pad_x, int pad_y, long long ycol,
+               const float* bias, int act, float* out, long long os_n, long long os_y, long long os_x,
+               long long os_c, fgt_stream_t stream);
+
 /* Depthwise k x k, stride k convolution (+bias) of the token grid [bt,h,w,ca+cb], zero-padded to
  * (gh*k, gw*k) -> fp32 [bt, gh*gw, ca+cb]. weight is the torch layout [C,1,k,k].
  * Replaces global_extract_k / global_extract_v, attention_flow.py:135,145. */
