@@ -87,6 +87,11 @@ def load():
     for fn in (lib.fgt_peer_alloc, lib.fgt_peer_free, lib.fgt_peer_export, lib.fgt_peer_import, lib.fgt_peer_unimport,
                lib.fgt_peer_barrier):
         fn.restype = ctypes.c_int
+    lib.fgt_regionfill_init.argtypes = [_c_p, _c_p, ci, ci, ci, _c_p, _c_p, _c_p, _c_p, _c_p]
+    lib.fgt_regionfill_iters.argtypes = [_c_p, ci, ci, ci, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, ci, ci, _c_p]
+    lib.fgt_regionfill_finish.argtypes = [_c_p, _c_p, cll, _c_p, _c_p, _c_p]
+    for fn in (lib.fgt_regionfill_init, lib.fgt_regionfill_iters, lib.fgt_regionfill_finish):
+        fn.restype = ctypes.c_int
     lib.fgt_tapsum.argtypes = [_c_p, ci, ci, ci, ci, ci, ci, ci, ci, cll, _c_p, ci, _c_p, cll, cll, cll, cll, _c_p]
     lib.fgt_tapsum.restype = ctypes.c_int
     lib.fgt_dwpool.argtypes = [_c_p, ci, _c_p, ci, ci, ci, ci, ci, ci, ci, _c_p, _c_p, _c_p, _c_p]

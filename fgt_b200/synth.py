@@ -353,3 +353,27 @@ def prop_inputs(seed=0, H=64, W=96, N=6):
         gx[mask[:, :, t], :, t] = 0
         gy[mask[:, :, t], :, t] = 0
     return gx, gy, mask, flow_f, flow_b
+
+
+def regionfill_inputs(seed=0, B=4, H=48, W=64):
+    """Images [B,H,W] float32 (smooth flow-like fields) and hole masks [B,H,W] bool exercising the cases of
+    tool/utils/region_fill.py: interior box, blob touching the image border and a corner (3- and 2-neighbour
+    rows), several components, a one-pixel hole, an empty mask (last image when B >= 4)."""
+    import numpy as np
+    g = torch.Generator().manual_seed(seed)
+    img = (_smooth(torch.randn(B, 1, H, W, generator=g), k=9)[:, 0] * 20.0).numpy().astype(np.float32)
+    mask = np.zeros((B, H, W), dtype=bool)
+    for b in range(B):
+        if B >= 4 and b == B - 1:
+            continue                                     # empty mask: image returned unchanged
+        mask[b, H // 4 + b:H // 4 + b + H // 3, W // 5:W // 5 + W // 3 + 2 * b] = True
+        if b % 3 == 0:
+            mask[b, :H // 6, :W // 7] = True             # touches the top-left corner
+            mask[b, H - 1, W // 2] = True                # single pixel on the bottom border
+        if b % 3 == 1:
+            mask[b, H - H // 5:, W - W // 4:] = True     # touches the bottom-right corner
+            mask[b, 2, W - 1] = True
+        if b % 3 == 2:
+            mask[b, H // 2:H // 2 + 3, W - 6:] = True    # touches the right border only
+        img[b][mask[b]] = 0.0                            # the driver zeroes the flow under the mask
+    return img, mask

@@ -179,6 +179,25 @@ int fgt_rownorm_bcast(const float* a, int ca, int lda, const float* b, int cb, i
                       fgt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Region fill / flow diffusion (tool/utils/region_fill.py:7-138 with factor = 1, called per flow channel by
+ * diffusion(), tool/video_inpainting.py:44-52): for B images [B,H,W] fp64 and hole masks (uint8, non-zero =
+ * hole) solve, inside each mask, the discrete Laplace equation with the surrounding image values as
+ * boundary data and zero flux at the image border — batched matrix-free conjugate gradients in fp64
+ * instead of the reference's per-image sparse direct solve.
+ *   fgt_regionfill_init  : x = 0, r = p0 = right-hand side (region_fill.py:69-112), rr[0..B) = <r,r>
+ *   fgt_regionfill_iters : CG iterations k0 .. k0+iters-1; rr / pap are zero-initialised arrays of
+ *                          (max_iters+1)*B doubles (iteration k uses rr[k*B+b], pap[k*B+b], writes rr[(k+1)*B+b]);
+ *                          the host reads rr to decide convergence
+ *   fgt_regionfill_finish: out = x inside the mask, img outside (region_fill.py:15-16)
+ * All arrays are caller-owned device memory. */
+int fgt_regionfill_init(const double* img, const unsigned char* mask, int B, int H, int W, double* x, double* r,
+                        double* p0, double* rr, fgt_stream_t stream);
+int fgt_regionfill_iters(const unsigned char* mask, int B, int H, int W, double* x, double* r, double* p0, double* p1,
+                         double* ap, double* rr, double* pap, int k0, int iters, fgt_stream_t stream);
+int fgt_regionfill_finish(const double* img, const unsigned char* mask, long long total, const double* x, double* out,
+                          fgt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Peer memory for the multi-GPU exchange (no reference counterpart: the reference's inference is
  * single-device). One process per GPU; buffers are cudaMalloc'ed here (IPC-capable,
  * zero-initialised), exported as 64-byte CUDA IPC handles that the host side exchanges over its

@@ -176,7 +176,27 @@ def prop_case(name, H, W, N, thres, seed):
     print(name, "holes", int(mask.sum()), "tofill", int(rm.sum()), "saved")
 
 
+def regionfill_case(name, B, H, W, seed):
+    sys.path.insert(0, os.path.join(REF, "tool"))
+    from utils.region_fill import regionfill
+    from oracle import regionfill_oracle as RO
+    img, mask = synth.regionfill_inputs(seed=seed, B=B, H=H, W=W)
+    ref = np.stack([regionfill(img[b], mask[b]) for b in range(B)])
+    ora = np.stack([RO.regionfill(img[b], mask[b]) for b in range(B)])
+    err = np.abs(ref - ora).max()
+    assert err < 1e-9, err
+    import scipy
+    meta = dict(B=B, H=H, W=W, seed=seed, scipy=scipy.__version__, **VERSIONS)
+    assert np.array_equal(ref[~mask], img.astype(np.float64)[~mask])  # only holes change
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=np.array(repr(meta)), out_hole=ref[mask])
+    print(name, "holes", int(mask.sum()), "oracle vs reference max abs", err, "saved")
+
+
 if __name__ == "__main__":
+    if "--regionfill-only" in sys.argv:
+        regionfill_case("regionfill_small", 4, 48, 64, seed=5)
+        regionfill_case("regionfill_mid", 3, 120, 216, seed=6)
+        sys.exit(0)
     if "--prop-only" in sys.argv:
         prop_case("prop_small", 64, 96, 6, 5.0, seed=2)
         prop_case("prop_thres1", 48, 64, 4, 1.0, seed=3)

@@ -8,6 +8,7 @@ import os
 import sys
 import time
 
+import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -119,4 +120,23 @@ t0 = time.perf_counter()
 PO.get_flownn_gradient(gx, gy, mask, ff, fb, 5.0, 0.1)
 r["cpu_oracle_s"] = time.perf_counter() - t0
 res["prop_240x432x10"] = r
+# ---- flow diffusion (region fill) of the 2*(N-1) = 18 incomplete flows of a 10-frame 240x432 clip: one batch
+from fgt_b200 import regionfill as RF  # noqa: E402
+from oracle import regionfill_oracle as RFO  # noqa: E402
+img, mask = synth.regionfill_inputs(seed=8, B=18, H=240, W=432)
+mask[-1, 60:140, 100:260] = True          # the synthetic set leaves its last mask empty; use a plain box there
+img[-1][mask[-1]] = 0
+flows = np.stack([img, img[::-1].copy()], -1)
+for _ in range(2):
+    RF.diffusion(flows, mask[..., None])
+t0 = time.perf_counter()
+for _ in range(3):
+    got = RF.diffusion(flows, mask[..., None])
+r = dict(ms_per_clip_host_to_host=(time.perf_counter() - t0) / 3 * 1e3, solves=36,
+         cg_iterations=RF.regionfill_batch(img, mask, return_iters=True)[1], hole_fraction=float(mask.mean()))
+t0 = time.perf_counter()
+ref = RFO.diffusion(flows[:2], mask[:2, ..., None])
+r["cpu_oracle_s_per_clip"] = (time.perf_counter() - t0) * 9
+r["max_abs_diff_vs_oracle"] = float(max(np.abs(a - b).max() for a, b in zip(got[:2], ref)))
+res["diffusion_240x432_18flows"] = r
 print(json.dumps(res))
