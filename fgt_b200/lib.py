@@ -71,7 +71,7 @@ def load():
     lib.fgt_gemm_tc.restype = ctypes.c_int
     lib.fgt_attention.argtypes = [ctypes.POINTER(FgtAttnDesc), _c_p]
     lib.fgt_attention.restype = ctypes.c_int
-    ci, cf, cll = ctypes.c_int, ctypes.c_float, _c_ll
+    ci, cf, cll, cd_ = ctypes.c_int, ctypes.c_float, _c_ll, ctypes.c_double
     lib.fgt_pack_nchw.argtypes = [_c_p, ci, _c_p, ci, ci, ci, ci, ci, ci, _c_p, cll, _c_p]
     lib.fgt_im2col_nchw.argtypes = [_c_p, ci, _c_p, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, cf, cf, _c_p, cll, _c_p]
     lib.fgt_im2col_nchw.restype = ctypes.c_int
@@ -91,6 +91,14 @@ def load():
     lib.fgt_regionfill_iters.argtypes = [_c_p, ci, ci, ci, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, ci, ci, _c_p]
     lib.fgt_regionfill_finish.argtypes = [_c_p, _c_p, cll, _c_p, _c_p, _c_p]
     for fn in (lib.fgt_regionfill_init, lib.fgt_regionfill_iters, lib.fgt_regionfill_finish):
+        fn.restype = ctypes.c_int
+    lib.fgt_poisson_setup.argtypes = [_c_p] * 6 + [ci, ci, ci, _c_p, _c_p, _c_p, _c_p]
+    lib.fgt_poisson_iters.argtypes = [_c_p, ci, ci, ci] + [_c_p] * 8 + [ci, ci, cd_, cd_, cd_, ci, _c_p]
+    lib.fgt_poisson_unfilled.argtypes = [_c_p, _c_p, ci, ci, ci, _c_p, _c_p]
+    lib.fgt_poisson_finish.argtypes = [_c_p, _c_p, _c_p, ci, ci, ci, _c_p, _c_p, _c_p, _c_p]
+    lib.fgt_poisson_advance_host.argtypes = [_c_p, _c_p, _c_p, ci, cd_, cd_, cd_, cd_, cd_, cd_, ci]
+    for fn in (lib.fgt_poisson_setup, lib.fgt_poisson_iters, lib.fgt_poisson_unfilled, lib.fgt_poisson_finish,
+               lib.fgt_poisson_advance_host):
         fn.restype = ctypes.c_int
     lib.fgt_tapsum.argtypes = [_c_p, ci, ci, ci, ci, ci, ci, ci, ci, cll, _c_p, ci, _c_p, cll, cll, cll, cll, _c_p]
     lib.fgt_tapsum.restype = ctypes.c_int

@@ -377,3 +377,42 @@ def regionfill_inputs(seed=0, B=4, H=48, W=64):
             mask[b, H // 2:H // 2 + 3, W - 6:] = True    # touches the right border only
         img[b][mask[b]] = 0.0                            # the driver zeroes the flow under the mask
     return img, mask
+
+
+# ----------------------------------------------------------------------------------------------
+# Poisson blending (Poisson_blend_img)
+# ----------------------------------------------------------------------------------------------
+def poisson_inputs(seed=0, F=3, H=64, W=96, with_edge=False):
+    """numpy inputs shaped like the driver's per-frame call (tool/video_inpainting.py:645-656), stacked over F
+    frames: target frames [F,H,W,3] float32 in [0,1] (zero inside the hole), forward-difference gradients
+    gx [F,H,W-1,3] / gy [F,H-1,W,3] float32 (source gradients + noise, i.e. not integrable: the system is
+    genuinely over-determined), hole masks [F,H,W] bool (interior box, a component touching the bottom-right
+    corner, a one-pixel hole; the last frame of F >= 3 has an empty hole), gradient masks [F,H,W] bool (a solid
+    block inside the box = gradients unknown there, plus one small component entirely without gradients) and,
+    with_edge, an edge map [F,H,W] float32 (a line crossing the box)."""
+    import numpy as np
+    g = torch.Generator().manual_seed(seed)
+    src = _smooth(torch.rand(F, 3, H, W, generator=g), k=9)
+    src = (src - src.amin()) / (src.amax() - src.amin())
+    src = (src.permute(0, 2, 3, 1) + 0.05 * torch.randn(F, H, W, 3, generator=g)).clamp(0, 1).numpy().astype(np.float32)
+    hole = np.zeros((F, H, W), dtype=bool)
+    gm = np.zeros((F, H, W), dtype=bool)
+    for f in range(F):
+        if F >= 3 and f == F - 1:
+            continue
+        y0, x0 = H // 4 + f, W // 5 + 2 * f
+        hole[f, y0:y0 + H // 3, x0:x0 + W // 3] = True
+        hole[f, H - H // 5:, W - W // 4:] = True
+        hole[f, 2, W // 2] = True
+        hole[f, H // 8:H // 8 + 3, W - 9:W - 5] = True
+        gm[f, y0 + H // 8:y0 + H // 5, x0 + W // 8:x0 + W // 5] = True
+        gm[f, H // 8 - 1:H // 8 + 4, W - 10:W - 4] = True       # this component has no usable gradient at all
+    trg = src.copy()
+    trg[hole] = 0
+    gx = (np.diff(src, axis=2) + 0.02 * torch.randn(F, H, W - 1, 3, generator=g).numpy()).astype(np.float32)
+    gy = (np.diff(src, axis=1) + 0.02 * torch.randn(F, H - 1, W, 3, generator=g).numpy()).astype(np.float32)
+    if not with_edge:
+        return trg, gx, gy, hole, gm
+    edge = np.zeros((F, H, W), dtype=np.float32)
+    edge[:, H // 3, :] = 1.0
+    return trg, gx, gy, hole, gm, edge

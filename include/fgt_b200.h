@@ -198,6 +198,38 @@ int fgt_regionfill_finish(const double* img, const unsigned char* mask, long lon
                           fgt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Gradient-domain (Poisson) blending (tool/utils/Poisson_blend_img.py:19-270: Poisson_blend_img, solvePoisson,
+ * constructEquation; called per frame at tool/video_inpainting.py:645-656): F frames x 3 channels solved together,
+ * matrix-free, by LSQR with scipy's recurrences and stopping tests (the reference calls
+ * scipy.sparse.linalg.lsqr with default tolerances, so its answer is the iterate at which that rule fires).
+ * All vectors fp64, channels-last; caller-owned, ZERO-INITIALISED device memory unless noted:
+ *   trg [F,H,W,3], gx [F,H,W-1,3], gy [F,H-1,W,3] (forward differences); hole / gmask / edge uint8 [F,H,W]
+ *   (gmask, edge may be NULL = all zero); code uint8 [F,H,W]; u [F,4,H*W,3]; v, w, x [F,H*W,3];
+ *   bb, aa, ww: (max_iters+2) * 3F per-iteration sums (slot k*3F + s); state [2, 3F, 16] (ping-pong by iteration
+ *   parity; per system s = 3*frame + channel: [12] = stopped, [13] = scipy's istop, [14] = itn).
+ *   fgt_poisson_setup   : equation codes, u = b, bb[0] = |b|^2                    (constructEquation :176-266)
+ *   fgt_poisson_iters   : k = k0 .. k0+iters-1; k = 0 finishes the set-up (v = A^T u / alfa, w = v), k >= 1 is
+ *                         LSQR iteration k; two kernels per k; systems that have stopped stay frozen
+ *   fgt_poisson_unfilled: the two raster sweeps of the connectivity check (:139-172) -> clr [2,F,H,W]
+ *   fgt_poisson_finish  : out = hole ? float64(float32(x)) : trg (:29,40-44); unf = hole & !clr[0] & !clr[1]
+ *                         (unf / clr may be NULL)
+ *   fgt_poisson_advance_host: HOST-ONLY — runs the scalar recurrence of one iteration (the same
+ *                         __host__ __device__ function the kernels call) on 16-double host states; step_out_host
+ *                         = {t1, t2, vscale, alfa*uscale, skip_all, skip_u}. For tests of the stopping logic. */
+int fgt_poisson_setup(const double* trg, const double* gx, const double* gy, const unsigned char* hole,
+                      const unsigned char* gmask, const unsigned char* edge, int F, int H, int W, unsigned char* code,
+                      double* u, double* bb, fgt_stream_t stream);
+int fgt_poisson_iters(const unsigned char* code, int F, int H, int W, double* u, double* v, double* w, double* x,
+                      double* bb, double* aa, double* ww, double* state, int k0, int iters, double atol, double btol,
+                      double conlim, int iter_lim, fgt_stream_t stream);
+int fgt_poisson_unfilled(const unsigned char* hole, const unsigned char* gmask, int F, int H, int W, unsigned char* clr,
+                         fgt_stream_t stream);
+int fgt_poisson_finish(const double* trg, const unsigned char* hole, const double* x, int F, int H, int W, double* out,
+                       const unsigned char* clr, unsigned char* unf, fgt_stream_t stream);
+int fgt_poisson_advance_host(const double* prev_host, double* cur_host, double* step_out_host, int k, double bbk,
+                             double aak, double wwk, double atol, double btol, double conlim, int iter_lim);
+
+/* ------------------------------------------------------------------------------------------
  * Peer memory for the multi-GPU exchange (no reference counterpart: the reference's inference is
  * single-device). One process per GPU; buffers are cudaMalloc'ed here (IPC-capable,
  * zero-initialised), exported as 64-byte CUDA IPC handles that the host side exchanges over its

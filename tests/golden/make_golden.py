@@ -192,7 +192,38 @@ def regionfill_case(name, B, H, W, seed):
     print(name, "holes", int(mask.sum()), "oracle vs reference max abs", err, "saved")
 
 
+def poisson_case(name, F, H, W, seed, with_edge):
+    sys.path.insert(0, os.path.join(REF, "tool"))
+    from utils.Poisson_blend_img import Poisson_blend_img
+    from oracle import poisson_oracle as PO
+    inp = synth.poisson_inputs(seed=seed, F=F, H=H, W=W, with_edge=with_edge)
+    trg, gx, gy, hole, gm = inp[:5]
+    blends, unfs, err = [], [], 0.0
+    for f in range(F):
+        if not hole[f].any():                      # the driver skips frames without a hole (video_inpainting.py:647)
+            blends.append(trg[f].astype(np.float64)); unfs.append(hole[f]); continue
+        kw = dict(edge=inp[5][f]) if with_edge else {}
+        rb, ru = Poisson_blend_img(trg[f], gx[f], gy[f], hole[f], gm[f], **kw)
+        ob, ou = PO.poisson_blend(trg[f], gx[f], gy[f], hole[f], gm[f], kw.get("edge"))
+        assert rb.dtype == np.float64 and ru.dtype == np.bool_ and np.array_equal(ru, ou)
+        assert np.array_equal(rb[~hole[f]], trg[f].astype(np.float64)[~hole[f]])      # only holes change
+        err = max(err, np.abs(rb - ob).max())
+        blends.append(rb); unfs.append(ru)
+    assert err < 5e-6, err
+    import scipy
+    blend, unf = np.stack(blends), np.stack(unfs)
+    meta = dict(F=F, H=H, W=W, seed=seed, with_edge=with_edge, scipy=scipy.__version__, **VERSIONS)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), meta=np.array(repr(meta)), blend_hole=blend[hole],
+                        unfilled=np.packbits(unf))
+    print(name, "holes", int(hole.sum()), "unfilled", int(unf.sum()), "oracle vs reference max abs", err, "saved")
+
+
 if __name__ == "__main__":
+    if "--poisson-only" in sys.argv:
+        poisson_case("poisson_small", 3, 64, 96, seed=7, with_edge=False)
+        poisson_case("poisson_edge", 2, 48, 64, seed=8, with_edge=True)
+        poisson_case("poisson_mid", 2, 120, 216, seed=9, with_edge=False)
+        sys.exit(0)
     if "--regionfill-only" in sys.argv:
         regionfill_case("regionfill_small", 4, 48, 64, seed=5)
         regionfill_case("regionfill_mid", 3, 120, 216, seed=6)
