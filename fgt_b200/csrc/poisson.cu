@@ -188,14 +188,16 @@ __global__ void psn_setup_kernel(const double* __restrict__ trg, const double* _
                                  const double* __restrict__ gy, const unsigned char* __restrict__ hole,
                                  const unsigned char* __restrict__ gmask, const unsigned char* __restrict__ edge, int H,
                                  int W, int S, unsigned char* __restrict__ code, double* __restrict__ u,
-                                 double* __restrict__ bb) {
+                                 double* __restrict__ bb, int* __restrict__ list, int* __restrict__ cnt) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ double red[kPsnC][kPsnThreads / 32];
+  __shared__ int s_woff[kPsnThreads / 32], s_base;
   const int f = blockIdx.y, HW = H * W;
   const long long fb = static_cast<long long>(f) * HW;
   const int i = blockIdx.x * kPsnThreads + threadIdx.x;
   double acc[kPsnC] = {0.0, 0.0, 0.0};
+  bool owns = false;
   if (i < HW) {
     unsigned cd = 0;
     if (hole[fb + i]) {
@@ -224,6 +226,27 @@ __global__ void psn_setup_kernel(const double* __restrict__ trg, const double* _
       }
     }
     code[fb + i] = static_cast<unsigned char>(cd);
+    owns = (cd & 15u) != 0u;
+  }
+  // compaction: pixels owning equations are appended to list[f] (raster order inside a block, blocks in
+  // arrival order), so the iteration kernels only launch threads that have work
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned bal = __ballot_sync(0xffffffffu, owns);
+    if (lane == 0) s_woff[warp] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int k = 0; k < kPsnThreads / 32; ++k) {
+        const int c = s_woff[k];
+        s_woff[k] = tot;
+        tot += c;
+      }
+      s_base = tot ? atomicAdd(&cnt[f], tot) : 0;
+    }
+    __syncthreads();
+    if (owns) list[fb + s_base + s_woff[warp] + __popc(bal & ((1u << lane) - 1u))] = i;
+    __syncthreads();
   }
   psn_block_sum(acc, red);
   if (threadIdx.x == 0)
@@ -231,7 +254,8 @@ __global__ void psn_setup_kernel(const double* __restrict__ trg, const double* _
       if (acc[c] != 0.0) atomicAdd(&bb[f * kPsnC + c], acc[c]);
 }
 
-__global__ void psn_v_kernel(const unsigned char* __restrict__ code, int H, int W, int S, const double* __restrict__ u,
+__global__ void psn_v_kernel(const unsigned char* __restrict__ code, const int* __restrict__ list,
+                             const int* __restrict__ cnt, int H, int W, int S, const double* __restrict__ u,
                              double* __restrict__ v, const double* __restrict__ bb, double* __restrict__ aa,
                              const double* __restrict__ state, int k) {
   pdl_launch_dependents();
@@ -252,9 +276,10 @@ __global__ void psn_v_kernel(const unsigned char* __restrict__ code, int H, int 
   }
   __syncthreads();
   const long long fb = static_cast<long long>(f) * HW;
-  const int i = blockIdx.x * kPsnThreads + threadIdx.x;
+  const int j = blockIdx.x * kPsnThreads + threadIdx.x;
+  const int i = j < cnt[f] ? list[fb + j] : -1;
   double acc[kPsnC] = {0.0, 0.0, 0.0};
-  const unsigned cd = i < HW ? code[fb + i] : 0u;
+  const unsigned cd = i >= 0 ? code[fb + i] : 0u;
   if (cd & 15u) {
     double s[kPsnC] = {0.0, 0.0, 0.0};
 #pragma unroll
@@ -284,7 +309,8 @@ __global__ void psn_v_kernel(const unsigned char* __restrict__ code, int H, int 
       if (acc[c] != 0.0) atomicAdd(&aa[static_cast<long long>(k) * S + f * kPsnC + c], acc[c]);
 }
 
-__global__ void psn_ux_kernel(const unsigned char* __restrict__ code, int H, int W, int S, double* __restrict__ u,
+__global__ void psn_ux_kernel(const unsigned char* __restrict__ code, const int* __restrict__ list,
+                              const int* __restrict__ cnt, int H, int W, int S, double* __restrict__ u,
                               const double* __restrict__ v, double* __restrict__ w, double* __restrict__ x,
                               double* __restrict__ bb, const double* __restrict__ aa, double* __restrict__ ww,
                               double* __restrict__ state, int k, double atol, double btol, double ctol, int iter_lim) {
@@ -308,9 +334,10 @@ __global__ void psn_ux_kernel(const unsigned char* __restrict__ code, int H, int
   }
   __syncthreads();
   const long long fb = static_cast<long long>(f) * HW;
-  const int i = blockIdx.x * kPsnThreads + threadIdx.x;
+  const int j = blockIdx.x * kPsnThreads + threadIdx.x;
+  const int i = j < cnt[f] ? list[fb + j] : -1;
   double accw[kPsnC] = {0.0, 0.0, 0.0}, accu[kPsnC] = {0.0, 0.0, 0.0};
-  const unsigned cd = i < HW ? code[fb + i] : 0u;
+  const unsigned cd = i >= 0 ? code[fb + i] : 0u;
   if (cd & 15u) {
     const double* vp = v + (fb + i) * kPsnC;
     double* wp = w + (fb + i) * kPsnC;
@@ -427,28 +454,33 @@ static dim3 psn_grid(int F, int H, int W) { return dim3((H * W + kPsnThreads - 1
 
 extern "C" int fgt_poisson_setup(const double* trg, const double* gx, const double* gy, const unsigned char* hole,
                                  const unsigned char* gmask, const unsigned char* edge, int F, int H, int W,
-                                 unsigned char* code, double* u, double* bb, fgt_stream_t stream) {
-  FGT_REQUIRE(trg && gx && gy && hole && code && u && bb && F >= 1 && H >= 2 && W >= 2, FGT_ERR_ARG,
+                                 unsigned char* code, double* u, double* bb, int* list, int* cnt,
+                                 fgt_stream_t stream) {
+  FGT_REQUIRE(trg && gx && gy && hole && code && u && bb && list && cnt && F >= 1 && H >= 2 && W >= 2, FGT_ERR_ARG,
               "poisson_setup: bad argument");
   launch_k(psn_setup_kernel, psn_grid(F, H, W), dim3(kPsnThreads), 0, reinterpret_cast<cudaStream_t>(stream), trg, gx,
-           gy, hole, gmask, edge, H, W, F * kPsnC, code, u, bb);
+           gy, hole, gmask, edge, H, W, F * kPsnC, code, u, bb, list, cnt);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;
 }
 
-extern "C" int fgt_poisson_iters(const unsigned char* code, int F, int H, int W, double* u, double* v, double* w,
-                                 double* x, double* bb, double* aa, double* ww, double* state, int k0, int iters,
-                                 double atol, double btol, double conlim, int iter_lim, fgt_stream_t stream) {
-  FGT_REQUIRE(code && u && v && w && x && bb && aa && ww && state && F >= 1 && k0 >= 0 && iters >= 1, FGT_ERR_ARG,
-              "poisson_iters: bad argument");
+extern "C" int fgt_poisson_iters(const unsigned char* code, const int* list, const int* cnt, int max_cnt, int F, int H,
+                                 int W, double* u, double* v, double* w, double* x, double* bb, double* aa, double* ww,
+                                 double* state, int k0, int iters, double atol, double btol, double conlim,
+                                 int iter_lim, fgt_stream_t stream) {
+  FGT_REQUIRE(code && list && cnt && u && v && w && x && bb && aa && ww && state && F >= 1 && k0 >= 0 && iters >= 1 &&
+                  max_cnt >= 0 && max_cnt <= H * W,
+              FGT_ERR_ARG, "poisson_iters: bad argument");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const dim3 grid = psn_grid(F, H, W);
+  // one block column even when no pixel owns an equation: block 0 of every frame carries the scalar state
+  const dim3 grid(max_cnt > 0 ? (max_cnt + kPsnThreads - 1) / kPsnThreads : 1, F);
   const int S = F * kPsnC;
   const double ctol = conlim > 0.0 ? 1.0 / conlim : 0.0;
   for (int k = k0; k < k0 + iters; ++k) {
-    launch_k(psn_v_kernel, grid, dim3(kPsnThreads), 0, st, code, H, W, S, static_cast<const double*>(u), v,
+    launch_k(psn_v_kernel, grid, dim3(kPsnThreads), 0, st, code, list, cnt, H, W, S, static_cast<const double*>(u), v,
              static_cast<const double*>(bb), aa, static_cast<const double*>(state), k);
-    launch_k(psn_ux_kernel, grid, dim3(kPsnThreads), 0, st, code, H, W, S, u, static_cast<const double*>(v), w, x, bb,
+    launch_k(psn_ux_kernel, grid, dim3(kPsnThreads), 0, st, code, list, cnt, H, W, S, u, static_cast<const double*>(v), w, x,
+             bb,
              static_cast<const double*>(aa), ww, state, k, atol, btol, ctol, iter_lim);
   }
   FGT_CUDA(cudaGetLastError());

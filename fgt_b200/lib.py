@@ -92,13 +92,19 @@ def load():
     lib.fgt_regionfill_finish.argtypes = [_c_p, _c_p, cll, _c_p, _c_p, _c_p]
     for fn in (lib.fgt_regionfill_init, lib.fgt_regionfill_iters, lib.fgt_regionfill_finish):
         fn.restype = ctypes.c_int
-    lib.fgt_poisson_setup.argtypes = [_c_p] * 6 + [ci, ci, ci, _c_p, _c_p, _c_p, _c_p]
-    lib.fgt_poisson_iters.argtypes = [_c_p, ci, ci, ci] + [_c_p] * 8 + [ci, ci, cd_, cd_, cd_, ci, _c_p]
+    lib.fgt_poisson_setup.argtypes = [_c_p] * 6 + [ci, ci, ci, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p]
+    lib.fgt_poisson_iters.argtypes = [_c_p, _c_p, _c_p, ci, ci, ci, ci] + [_c_p] * 8 + [ci, ci, cd_, cd_, cd_, ci, _c_p]
     lib.fgt_poisson_unfilled.argtypes = [_c_p, _c_p, ci, ci, ci, _c_p, _c_p]
     lib.fgt_poisson_finish.argtypes = [_c_p, _c_p, _c_p, ci, ci, ci, _c_p, _c_p, _c_p, _c_p]
     lib.fgt_poisson_advance_host.argtypes = [_c_p, _c_p, _c_p, ci, cd_, cd_, cd_, cd_, cd_, cd_, ci]
     for fn in (lib.fgt_poisson_setup, lib.fgt_poisson_iters, lib.fgt_poisson_unfilled, lib.fgt_poisson_finish,
                lib.fgt_poisson_advance_host):
+        fn.restype = ctypes.c_int
+    lib.fgt_plane_max.argtypes = [_c_p, ci, cll, _c_p, _c_p]
+    lib.fgt_window_gather.argtypes = [_c_p, _c_p, _c_p, _c_p, _c_p, ci, ci, ci, _c_p, _c_p, _c_p, _c_p]
+    lib.fgt_window_compose.argtypes = [_c_p, _c_p, _c_p, _c_p, _c_p, ci, ci, ci, _c_p, _c_p]
+    lib.fgt_comp_to_u8.argtypes = [_c_p, cll, _c_p, _c_p]
+    for fn in (lib.fgt_plane_max, lib.fgt_window_gather, lib.fgt_window_compose, lib.fgt_comp_to_u8):
         fn.restype = ctypes.c_int
     lib.fgt_tapsum.argtypes = [_c_p, ci, ci, ci, ci, ci, ci, ci, ci, cll, _c_p, ci, _c_p, cll, cll, cll, cll, _c_p]
     lib.fgt_tapsum.restype = ctypes.c_int

@@ -61,20 +61,24 @@ def poisson_blend_batch(trg, gx, gy, hole, gmask=None, edge=None, device=None, r
     v, w, x = z64(F, H * W, C), z64(F, H * W, C), z64(F, H * W, C)
     bb, aa, ww = z64((max_iters + 2) * S), z64((max_iters + 2) * S), z64((max_iters + 2) * S)
     state = z64(2, S, 16)
+    plist = torch.empty(F, H * W, dtype=torch.int32, device=dev)
+    cnt = torch.zeros(F, dtype=torch.int32, device=dev)
     L = lib.load()
     sp = lib.stream_ptr
     lib.check(L.fgt_poisson_setup(trg.data_ptr(), gx.data_ptr(), gy.data_ptr(), hole.data_ptr(), _ptr(gmask), _ptr(edge),
-                                  F, H, W, code.data_ptr(), u.data_ptr(), bb.data_ptr(), sp()), "fgt_poisson_setup")
+                                  F, H, W, code.data_ptr(), u.data_ptr(), bb.data_ptr(), plist.data_ptr(), cnt.data_ptr(),
+                                  sp()), "fgt_poisson_setup")
     clr = torch.empty(2, F, H, W, dtype=torch.uint8, device=dev)
     lib.check(L.fgt_poisson_unfilled(hole.data_ptr(), _ptr(gmask), F, H, W, clr.data_ptr(), sp()), "fgt_poisson_unfilled")
     lib.COUNTERS["launches"] += 2
     iter_lim = 2 * H * W
+    max_cnt = int(cnt.max())                           # pixels owning equations, largest frame (one host sync)
     k = 0
     while True:
         n = min(CHUNK, max_iters + 1 - k)
         if n <= 0:
             raise RuntimeError(f"poisson: LSQR did not stop within {max_iters} iterations")
-        lib.check(L.fgt_poisson_iters(code.data_ptr(), F, H, W, u.data_ptr(), v.data_ptr(), w.data_ptr(), x.data_ptr(),
+        lib.check(L.fgt_poisson_iters(code.data_ptr(), plist.data_ptr(), cnt.data_ptr(), max_cnt, F, H, W, u.data_ptr(), v.data_ptr(), w.data_ptr(), x.data_ptr(),
                                       bb.data_ptr(), aa.data_ptr(), ww.data_ptr(), state.data_ptr(), k, n,
                                       atol, btol, conlim, iter_lim, sp()), "fgt_poisson_iters")
         lib.COUNTERS["launches"] += 2 * n

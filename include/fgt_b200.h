@@ -207,7 +207,10 @@ int fgt_regionfill_finish(const double* img, const unsigned char* mask, long lon
  *   (gmask, edge may be NULL = all zero); code uint8 [F,H,W]; u [F,4,H*W,3]; v, w, x [F,H*W,3];
  *   bb, aa, ww: (max_iters+2) * 3F per-iteration sums (slot k*3F + s); state [2, 3F, 16] (ping-pong by iteration
  *   parity; per system s = 3*frame + channel: [12] = stopped, [13] = scipy's istop, [14] = itn).
- *   fgt_poisson_setup   : equation codes, u = b, bb[0] = |b|^2                    (constructEquation :176-266)
+ *   fgt_poisson_setup   : equation codes, u = b, bb[0] = |b|^2 (constructEquation :176-266); appends the pixels
+ *                         that own equations to list [F,H*W] int32 and counts them in cnt [F] (zero-initialised) —
+ *                         the host reads max(cnt) once and passes it as max_cnt, so the iteration kernels launch
+ *                         threads for those pixels only
  *   fgt_poisson_iters   : k = k0 .. k0+iters-1; k = 0 finishes the set-up (v = A^T u / alfa, w = v), k >= 1 is
  *                         LSQR iteration k; two kernels per k; systems that have stopped stay frozen
  *   fgt_poisson_unfilled: the two raster sweeps of the connectivity check (:139-172) -> clr [2,F,H,W]
@@ -218,16 +221,37 @@ int fgt_regionfill_finish(const double* img, const unsigned char* mask, long lon
  *                         = {t1, t2, vscale, alfa*uscale, skip_all, skip_u}. For tests of the stopping logic. */
 int fgt_poisson_setup(const double* trg, const double* gx, const double* gy, const unsigned char* hole,
                       const unsigned char* gmask, const unsigned char* edge, int F, int H, int W, unsigned char* code,
-                      double* u, double* bb, fgt_stream_t stream);
-int fgt_poisson_iters(const unsigned char* code, int F, int H, int W, double* u, double* v, double* w, double* x,
-                      double* bb, double* aa, double* ww, double* state, int k0, int iters, double atol, double btol,
-                      double conlim, int iter_lim, fgt_stream_t stream);
+                      double* u, double* bb, int* list, int* cnt, fgt_stream_t stream);
+int fgt_poisson_iters(const unsigned char* code, const int* list, const int* cnt, int max_cnt, int F, int H, int W,
+                      double* u, double* v, double* w, double* x, double* bb, double* aa, double* ww, double* state,
+                      int k0, int iters, double atol, double btol, double conlim, int iter_lim, fgt_stream_t stream);
 int fgt_poisson_unfilled(const unsigned char* hole, const unsigned char* gmask, int F, int H, int W, unsigned char* clr,
                          fgt_stream_t stream);
 int fgt_poisson_finish(const double* trg, const unsigned char* hole, const double* x, int F, int H, int W, double* out,
                        const unsigned char* clr, unsigned char* unf, fgt_stream_t stream);
 int fgt_poisson_advance_host(const double* prev_host, double* cur_host, double* step_out_host, int k, double bbk,
                              double aak, double wwk, double atol, double btol, double conlim, int iter_lim);
+
+/* ------------------------------------------------------------------------------------------
+ * The FGT stage's window loop around Model.forward (tool/video_inpainting.py:686-745), device-resident instead of
+ * one host round trip per window and frame. Clip tensors: frames [N,3,H,W] float in [0,1] (np2tensor(frameBlends),
+ * :691), masks [N,H,W] uint8 (:692-694), flows [N,2,H,W] float (completed forward flows, last one repeated, :702-707).
+ *   fgt_plane_max     : out[i] = max over plane i of x [planes, plane_size]   (norm_flows :402-407: per frame & channel)
+ *   fgt_window_gather : model inputs of one window — ids [t] (device int32) are neighbour + reference frame ids (:711-717):
+ *                       out_frames [t,3,H,W] = (frames*2-1)*(1-mask) (:695,:721), out_flows [t,2,H,W] = flows/fmax,
+ *                       out_masks [t,1,H,W]
+ *   fgt_window_compose: filled [t,3,H,W] = Model.forward output; for the first k (= neighbour) frames
+ *                       comp[id] = u8((out+1)/2*255)*mask + u8(frame*255)*(1-mask) (:725-733), stored if first[i] else
+ *                       averaged 0.5/0.5 with the stored value (:734-741); comp [N,H,W,3] float
+ *   fgt_comp_to_u8    : the final astype(uint8) (:745)
+ * Same IEEE single-precision operations in the same order as the reference: bit-identical given the same model output. */
+int fgt_plane_max(const float* x, int planes, long long plane_size, float* out, fgt_stream_t stream);
+int fgt_window_gather(const float* frames, const unsigned char* masks, const float* flows, const float* fmax,
+                      const int* ids, int t, int H, int W, float* out_frames, float* out_flows, float* out_masks,
+                      fgt_stream_t stream);
+int fgt_window_compose(const float* filled, const float* frames, const unsigned char* masks, const int* ids,
+                       const unsigned char* first, int k, int H, int W, float* comp, fgt_stream_t stream);
+int fgt_comp_to_u8(const float* comp, long long total, unsigned char* out, fgt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Peer memory for the multi-GPU exchange (no reference counterpart: the reference's inference is

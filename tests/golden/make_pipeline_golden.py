@@ -1,0 +1,138 @@
+"""Runs the UNMODIFIED reference driver `tool/video_inpainting.py::video_inpainting(args)` end to end on the CPU
+(object-removal mode) on a small synthetic clip and records what crosses two stage boundaries:
+
+* every `Poisson_blend_img` call (inputs after real propagation + binary_fill_holes, outputs)  -> pipeline_poisson.npz
+* the FGT stage (tool/video_inpainting.py:686-745): the three `np2tensor(..., near="t")` inputs (frameBlends,
+  mask, completed forward flows) and the frames handed to the video writer                    -> pipeline_clip.npz
+
+    python tests/golden/make_pipeline_golden.py
+
+Only available in the build container (/root/reference). The driver imports three packages that are not in
+this image (cvbase: .flo visualisation, imageio: video writer, skimage.feature.canny: unused in this mode); they
+are stubbed, `imageio.mimwrite` being the hook that captures the final frames. RAFT uses the real
+raft-things.pth; FGT / LAFC checkpoints (not in the repository) are the seeded synthetic weights of
+fgt_b200.synth written to temporary checkpoint directories in the layout `initialize_FGT/LAFC` expects.
+"""
+import argparse
+import contextlib
+import io
+import os
+import shutil
+import sys
+import tempfile
+import types
+
+import numpy as np
+import torch
+import yaml
+from PIL import Image
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from fgt_b200 import synth  # noqa: E402
+
+H, W, N = 64, 96, 7
+CAPTURE = {}
+
+
+def clip_frames(seed=5):
+    """N uint8 RGB frames: a smooth texture translating by (2, 1) px per frame, plus a moving box mask."""
+    g = torch.Generator().manual_seed(seed)
+    big = synth._smooth(torch.rand(1, 3, H + 64, W + 64, generator=g), k=7)[0]
+    big = (big - big.amin()) / (big.amax() - big.amin())
+    frames, masks = [], []
+    for i in range(N):
+        y0, x0 = 16 + i, 16 + 2 * i
+        fr = (big[:, y0:y0 + H, x0:x0 + W].permute(1, 2, 0).numpy() * 255).astype(np.uint8)
+        m = np.zeros((H, W), np.uint8)
+        m[20 + i:38 + i, 30 + 2 * i:52 + 2 * i] = 255
+        frames.append(fr)
+        masks.append(m)
+    return frames, masks
+
+
+def main():
+    for m in ("cvbase", "imageio", "skimage", "skimage.feature"):
+        sys.modules.setdefault(m, types.ModuleType(m))
+    sys.modules["skimage.feature"].canny = None
+    sys.modules["imageio"].mimwrite = lambda path, frames, **kw: CAPTURE.__setitem__("comp_frames", [np.array(f) for f in frames])
+    sys.path.insert(0, os.path.join(REF, "tool"))       # the script directory comes first when the driver is run
+    import video_inpainting as VI
+
+    tmp = tempfile.mkdtemp(prefix="fgt_pipeline_")
+    try:
+        frames, masks = clip_frames()
+        for d in ("frames", "masks", "fgt_ckpt", "lafc_ckpt", "out"):
+            os.makedirs(os.path.join(tmp, d))
+        for i, (fr, m) in enumerate(zip(frames, masks)):
+            Image.fromarray(fr).save(os.path.join(tmp, "frames", "%05d.png" % i))
+            Image.fromarray(m).save(os.path.join(tmp, "masks", "%05d.png" % i))
+        cfg = dict(synth.CFG_A)
+        cfg["input_resolution"] = (H, W)
+        fgt_sd = synth.make_state_dict(synth.fgt_param_shapes(cfg), seed=31)
+        torch.save({"model_state_dict": fgt_sd}, os.path.join(tmp, "fgt_ckpt", "fgt.tar"))
+        ycfg = {k: (list(v) if isinstance(v, tuple) else v) for k, v in cfg.items()}
+        ycfg["model"] = "model"
+        with open(os.path.join(tmp, "fgt_ckpt", "config.yaml"), "w") as fh:
+            yaml.safe_dump(ycfg, fh)
+        lafc_sd = synth.make_state_dict(synth.lafc_param_shapes(synth.CFG_LAFC), seed=32)
+        torch.save({"model_state_dict": lafc_sd}, os.path.join(tmp, "lafc_ckpt", "lafc.tar"))
+        with open(os.path.join(tmp, "lafc_ckpt", "config.yaml"), "w") as fh:
+            yaml.safe_dump(dict(synth.CFG_LAFC), fh)
+        opt = os.path.join(tmp, "opt.yaml")
+        with open(opt, "w") as fh:
+            yaml.safe_dump(dict(mode="object_removal", consistencyThres=5, alpha=0.1, flow_mask_dilates=3, frame_dilates=1), fh)
+        args = argparse.Namespace(
+            opt=opt, mode="object_removal", path=os.path.join(tmp, "frames"), path_mask=os.path.join(tmp, "masks"),
+            outroot=os.path.join(tmp, "out"), consistencyThres=5.0, alpha=0.1, Nonlocal=False,
+            raft_model=os.path.join(REF, "LAFC", "flowCheckPoint", "raft-things.pth"), small=False, mixed_precision=False,
+            alternate_corr=False, lafc_ckpts=os.path.join(tmp, "lafc_ckpt"), fgt_ckpts=os.path.join(tmp, "fgt_ckpt"),
+            H_scale=2, W_scale=2, imgH=H, imgW=W, flow_mask_dilates=3, frame_dilates=1, gpu=0, step=10, num_ref=-1,
+            neighbor_stride=5, vis_flows=False, vis_completed_flows=False, vis_prop=False, vis_frame=False)
+
+        # hooks: record, then call the unmodified function
+        t_calls, p_calls = [], []
+        ref_np2tensor, ref_poisson = VI.np2tensor, VI.Poisson_blend_img
+
+        def np2tensor(array, near="c"):
+            if near == "t":
+                t_calls.append(np.stack(array, 0).copy() if isinstance(array, list) else np.array(array))
+            return ref_np2tensor(array, near)
+
+        def poisson(*a, **kw):
+            out = ref_poisson(*a, **kw)
+            p_calls.append(([np.array(x) for x in a], [np.array(o) for o in out]))
+            return out
+
+        VI.np2tensor, VI.Poisson_blend_img = np2tensor, poisson
+        with contextlib.redirect_stdout(io.StringIO()):
+            VI.video_inpainting(args)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+    import cv2
+    import scipy
+    meta = dict(H=H, W=W, N=N, fgt_seed=31, lafc_seed=32, torch=torch.__version__, numpy=np.__version__,
+                scipy=scipy.__version__, cv2=cv2.__version__)
+    frame_blends, mask, flow_f = t_calls            # the three near="t" conversions of the FGT stage, in order
+    comp = np.stack(CAPTURE["comp_frames"])
+    assert frame_blends.shape == (N, H, W, 3) and mask.shape == (N, H, W, 1) and flow_f.shape == (N, H, W, 2)
+    assert comp.shape == (N, H, W, 3) and comp.dtype == np.uint8
+    # frame_blends as recorded are already RGB (the driver flips in place before np2tensor, :688-689)
+    np.savez_compressed(os.path.join(HERE, "pipeline_clip.npz"), meta=np.array(repr(meta)),
+                        frames_rgb=frame_blends, mask=np.packbits(mask.astype(bool)), flow_f=flow_f[:-1].astype(np.float32),
+                        comp=comp)
+    trg = np.stack([a[0] for a, _ in p_calls]); gx = np.stack([a[1] for a, _ in p_calls]); gy = np.stack([a[2] for a, _ in p_calls])
+    hole = np.stack([a[3] for a, _ in p_calls]); gm = np.stack([a[4] for a, _ in p_calls])
+    blend = np.stack([o[0] for _, o in p_calls]); unf = np.stack([o[1] for _, o in p_calls])
+    assert trg.dtype in (np.float32, np.float64) and gx.dtype == np.float32 and hole.dtype == np.bool_
+    np.savez_compressed(os.path.join(HERE, "pipeline_poisson.npz"), meta=np.array(repr(meta)), trg=trg, gx=gx, gy=gy,
+                        hole=np.packbits(hole), gmask=np.packbits(gm), blend_hole=blend[hole], unfilled=np.packbits(unf))
+    print("pipeline goldens saved:", len(p_calls), "Poisson calls, holes", int(hole.sum()), "unfilled", int(unf.sum()),
+          "| comp mean", comp.mean(), "| blend dtype", blend.dtype, "trg dtype", trg.dtype)
+
+
+if __name__ == "__main__":
+    main()

@@ -173,6 +173,35 @@ def test_sweep_prefix_formulation_matches_oracle():
         assert np.array_equal(unf, PO.unfilled_mask(h, m))
 
 
+def _pipeline_case():
+    """Driver-faithful inputs: the seven Poisson_blend_img calls of one run of the unmodified reference driver
+    (tests/golden/make_pipeline_golden.py) — gradients after real flow-guided propagation, gradient masks after
+    binary_fill_holes."""
+    g = load_golden("pipeline_poisson")
+    trg = g["trg"]
+    F, H, W = trg.shape[:3]
+    bits = lambda k: np.unpackbits(g[k])[:F * H * W].reshape(F, H, W).astype(bool)
+    return trg, g["gx"], g["gy"], bits("hole"), bits("gmask"), g["blend_hole"], bits("unfilled")
+
+
+def test_oracle_matches_reference_driver_poisson_calls():
+    trg, gx, gy, hole, gm, gold, gunf = _pipeline_case()
+    blend, unf, _ = _oracle_clip(trg, gx, gy, hole, gm, None)
+    assert np.array_equal(unf, gunf) and gunf.sum() > 0
+    assert np.abs(blend[hole] - gold).max() < 5e-6
+
+
+@pytest.mark.gpu
+def test_gpu_poisson_vs_reference_driver_calls():
+    from fgt_b200 import poisson as P
+    trg, gx, gy, hole, gm, gold, gunf = _pipeline_case()
+    out, unf = P.poisson_blend_batch(trg, gx, gy, hole, gm)
+    out, unf = out.cpu().numpy(), unf.cpu().numpy()
+    assert np.array_equal(unf, gunf)
+    assert np.abs(out[hole] - gold).max() < 5e-6
+    assert np.array_equal(out[~hole], trg.astype(np.float64)[~hole])
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", list(CASES))
