@@ -1,0 +1,234 @@
+"""The driver's object-removal pipeline (tool/video_inpainting.py:418-745, `video_inpainting(args)`) on arrays
+instead of directories, with every heavy stage on the GPU:
+
+    frames, masks ──► RAFT flows (batched pairs) ──► flow diffusion (batched CG) + LAFC completion
+                 ──► gradient propagation ──► Poisson blending (batched LSQR) ──► FGT windows + compositing
+
+Host-side remain exactly the calls the reference makes to third-party image code — `F.interpolate` of the input
+frames (:478-483), `cv2.resize` of flows and masks (:264-267,:544-546), `scipy.ndimage.binary_dilation /
+binary_fill_holes` (:549-561,:637-640) and `cv2.inpaint` (TELEA, :591-599,:663-671) — SURVEY §8f rank 3 lists
+their GPU equivalents as the next step. The stage implementations come from a backend object; `GpuBackend`
+(default) binds the fgt_b200 modules, and the parity tests plug the CPU oracle into the same glue, so the glue
+itself is verified against a full run of the unmodified reference driver (tests/golden/pipeline_*.npz).
+There is no CPU fallback in this module: GpuBackend raises without a CUDA device.
+"""
+import argparse
+
+import cv2
+import numpy as np
+import scipy.ndimage
+import torch
+import torch.nn.functional as F
+
+DEFAULTS = dict(imgH=256, imgW=432, flow_mask_dilates=8, frame_dilates=0, consistencyThres=5.0, alpha=0.1,
+                Nonlocal=False, step=10, num_ref=-1, neighbor_stride=5, raft_iters=20)
+
+
+def make_args(**kw):
+    """Namespace with the driver's argparse defaults (:764-855) overridden by keyword."""
+    unknown = set(kw) - set(DEFAULTS)
+    if unknown:
+        raise TypeError(f"unknown pipeline options: {sorted(unknown)}")
+    return argparse.Namespace(**{**DEFAULTS, **kw})
+
+
+def indices_gen(pivot, interval, frames, t):
+    """indicesGen (:90-100): `frames` indices centred on pivot, reflected at both ends of [0, t-1]."""
+    out = []
+    for i in range(-(frames // 2), frames // 2 + 1):
+        idx = abs(pivot + interval * i)
+        out.append(2 * (t - 1) - idx if idx > t - 1 else idx)
+    return out
+
+
+def gradient_mask(mask):
+    """gradient_mask (:74-87): the mask OR-ed with itself shifted up and left (pixels whose forward difference
+    touches the hole)."""
+    m = np.asarray(mask).astype(bool)
+    up = np.zeros_like(m); up[:-1] = m[1:]
+    left = np.zeros_like(m); left[:, :-1] = m[:, 1:]
+    return m | up | left
+
+
+# ------------------------------------------------------------------------------------------------ stages
+def load_clip(frames_u8, args):
+    """:470-490 — uint8 RGB frames [N,h,w,3] -> (video [N,3,imgH,imgW], video_flow [N,3,flowH,flowW]) float32 0..255.
+    RAFT sees frames at twice the working resolution when imgH < 350 (:440-443)."""
+    flow_hw = (args.imgH * 2, args.imgW * 2) if args.imgH < 350 else (args.imgH, args.imgW)
+    video, video_flow = [], []
+    for fr in frames_u8:
+        t = torch.from_numpy(np.ascontiguousarray(fr).astype(np.uint8)).permute(2, 0, 1).float().unsqueeze(0)
+        t = F.interpolate(t, size=(args.imgH, args.imgW), mode="bilinear", align_corners=False)
+        video.append(t)
+        video_flow.append(F.interpolate(t, size=flow_hw, mode="bilinear", align_corners=False))
+    return torch.cat(video, 0), torch.cat(video_flow, 0)
+
+
+def compute_flows(backend, video_flow, args, mode):
+    """calculate_flow (:232-283): RAFT on consecutive frames (forward i -> i+1, backward i+1 -> i), resized to the
+    working resolution with the flow vectors rescaled. Returns [imgH,imgW,2,N-1] float32."""
+    a, b = (video_flow[:-1], video_flow[1:]) if mode == "forward" else (video_flow[1:], video_flow[:-1])
+    flows = backend.raft_pairs(a, b, args.raft_iters)                   # [N-1,2,h,w]
+    out = np.empty((args.imgH, args.imgW, 2, 0), dtype=np.float32)
+    for i in range(flows.shape[0]):
+        flow = np.ascontiguousarray(flows[i].transpose(1, 2, 0))
+        h, w = flow.shape[:2]
+        if h != args.imgH or w != args.imgW:
+            flow = cv2.resize(flow, (args.imgW, args.imgH), cv2.INTER_LINEAR)   # same positional call as the driver
+            flow[:, :, 0] *= float(args.imgW) / float(w)
+            flow[:, :, 1] *= float(args.imgH) / float(h)
+        out = np.concatenate((out, flow[..., None]), axis=-1)
+    return out
+
+
+def prepare_masks(masks_u8, args):
+    """:539-567 — per-frame uint8 masks [N,h,w] (non-zero = hole) -> (mask, mask_dilated, flow_mask) bool [H,W,N]."""
+    mask, dilated, flow_mask = [], [], []
+    for m in masks_u8:
+        m = cv2.resize(np.ascontiguousarray(m).astype(np.uint8), dsize=(args.imgW, args.imgH), interpolation=cv2.INTER_NEAREST)
+        flow_mask.append(scipy.ndimage.binary_dilation(m, iterations=args.flow_mask_dilates) if args.flow_mask_dilates > 0 else m)
+        if args.frame_dilates > 0:
+            m = scipy.ndimage.binary_dilation(m, iterations=args.frame_dilates)
+        mask.append(m)
+        dilated.append(gradient_mask(m))
+    st = lambda xs: np.stack(xs, -1).astype(bool)
+    return st(mask), st(dilated), st(flow_mask)
+
+
+def complete_flows(backend, flows, flow_mask, mode, num_flows, flow_interval):
+    """complete_flow (:338-385): diffuse the holes of every flow, run LAFC on (pivot ± interval) triplets, keep the
+    network output inside the hole and the measured flow outside. flows [H,W,2,N-1] -> [H,W,2,N-1] float32."""
+    masks = np.moveaxis(flow_mask, -1, 0)[..., None]                     # [N,H,W,1]
+    masks = masks[:-1] if mode == "forward" else masks[1:]
+    fl = np.moveaxis(flows, -1, 0)                                       # [N-1,H,W,2]
+    diffused = backend.diffusion(fl, masks)                              # list of [H,W,2] float64
+    to_cthw = lambda a: np.ascontiguousarray(np.transpose(np.stack(a, 0) if isinstance(a, list) else a, (3, 0, 1, 2))).astype(np.float32)
+    fl_t, mk_t, df_t = to_cthw(fl), to_cthw(masks), to_cthw(diffused)    # [c,t,H,W]
+    t = df_t.shape[1]
+    triplets = [indices_gen(i, flow_interval, num_flows, t) for i in range(t)]
+    out = backend.lafc_complete(fl_t, mk_t, df_t, triplets, num_flows // 2)   # [t,2,H,W]
+    return np.ascontiguousarray(np.transpose(out, (2, 3, 1, 0)))
+
+
+def prepare_gradients(video, mask, mask_dilated):
+    """:583-614 — zero the hole (in place, like the driver), TELEA-inpaint it for a plausible initialisation, take
+    forward differences and zero them wherever they touch the hole. video [H,W,3,N] float32 (BGR, 0..1)."""
+    H, W, _, N = video.shape
+    gx = np.empty((H, W, 3, 0), dtype=np.float32)
+    gy = np.empty((H, W, 3, 0), dtype=np.float32)
+    for i in range(N):
+        img = video[:, :, :, i]
+        img[mask[:, :, i], :] = 0
+        img = cv2.inpaint((img * 255).astype(np.uint8), mask[:, :, i].astype(np.uint8), 3, cv2.INPAINT_TELEA).astype(np.float32) / 255.0
+        dx = np.concatenate((np.diff(img, axis=1), np.zeros((H, 1, 3), dtype=np.float32)), axis=1)
+        dy = np.concatenate((np.diff(img, axis=0), np.zeros((1, W, 3), dtype=np.float32)), axis=0)
+        gx = np.concatenate((gx, dx.reshape(H, W, 3, 1)), axis=-1)
+        gy = np.concatenate((gy, dy.reshape(H, W, 3, 1)), axis=-1)
+        gx[mask_dilated[:, :, i], :, i] = 0
+        gy[mask_dilated[:, :, i], :, i] = 0
+    return gx, gy
+
+
+def blend_frames(backend, video, gx, gy, mask, mask_gradient):
+    """:636-681 — fill the holes of the propagated-gradient mask, Poisson-blend every frame that still has a hole
+    (all of them in one batch), TELEA-inpaint what the blend could not reach, mark it green in the frames handed to
+    the transformer. Updates `video` and `mask` in place like the driver; returns the list of frames."""
+    H, W, _, N = video.shape
+    for i in range(N):
+        mask_gradient[:, :, i] = scipy.ndimage.binary_fill_holes(mask_gradient[:, :, i]).astype(bool)
+    todo = [i for i in range(N) if mask[:, :, i].sum() > 0]
+    blends = backend.poisson_frames([video[:, :, :, i] for i in todo], [gx[:, 0:W - 1, :, i] for i in todo],
+                                    [gy[0:H - 1, :, :, i] for i in todo], [mask[:, :, i] for i in todo],
+                                    [mask_gradient[:, :, i] for i in todo]) if todo else []
+    out = []
+    for i in range(N):
+        if i not in todo:
+            out.append(video[:, :, :, i])
+            continue
+        blend, unfilled = blends[todo.index(i)]
+        blend = np.clip(blend, 0, 1.0)
+        tmp = cv2.inpaint((blend * 255).astype(np.uint8), unfilled.astype(np.uint8), 3, cv2.INPAINT_TELEA).astype(np.float32) / 255.0
+        blend[unfilled, :] = tmp[unfilled, :]
+        video[:, :, :, i] = blend
+        mask[:, :, i] = unfilled
+        shown = blend.copy()
+        shown[unfilled, :] = [0, 1.0, 0]          # green = not filled by propagation (:678-679); masked out for the model
+        out.append(shown)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ backend
+class GpuBackend:
+    """Stage implementations on the fgt_b200 kernels. raft / lafc / fgt are the drop-in modules (already on the
+    device, weights loaded); lafc_config provides num_flows / flow_interval like the driver's LAFC yaml."""
+
+    def __init__(self, raft, lafc, fgt, device=None, raft_batch=4):
+        if not torch.cuda.is_available():
+            raise RuntimeError("fgt_b200.pipeline.GpuBackend needs a CUDA (sm_100a) device; there is no CPU fallback")
+        self.dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.raft, self.lafc, self.fgt = raft, lafc, fgt
+        self.raft_batch = raft_batch
+
+    def raft_pairs(self, img1, img2, iters):
+        outs = []
+        with torch.no_grad():
+            for s in range(0, img1.shape[0], self.raft_batch):
+                a, b = img1[s:s + self.raft_batch].to(self.dev), img2[s:s + self.raft_batch].to(self.dev)
+                _, up = self.raft(a, b, iters=iters, test_mode=True)
+                outs.append(up.float().cpu())
+        return torch.cat(outs, 0).numpy()
+
+    def diffusion(self, flows, masks):
+        from .regionfill import diffusion
+        return diffusion(flows, masks)
+
+    def lafc_complete(self, flows, masks, diffused, triplets, pivot):
+        fl, mk, df = (torch.from_numpy(a).to(self.dev).unsqueeze(0) for a in (flows, masks, diffused))   # [1,c,t,H,W]
+        out = []
+        with torch.no_grad():
+            for idx in triplets:
+                cand_masks = mk[:, :, idx]
+                res = self.lafc(df[:, :, idx], cand_masks, None)
+                res = res[0] if isinstance(res, (tuple, list)) else res
+                pm = cand_masks[:, :, pivot]
+                out.append(res * pm + fl[:, :, idx][:, :, pivot] * (1 - pm))
+        return torch.cat(out, 0).float().cpu().numpy()
+
+    def propagate(self, args, gx, gy, mask, mask_gradient, flow_f, flow_b):
+        from .propagation import get_flowNN_gradient
+        return get_flowNN_gradient(args, gx, gy, mask, mask_gradient, flow_f, flow_b, None, None, device=str(self.dev))
+
+    def poisson_frames(self, trg, gx, gy, hole, gmask):
+        from .poisson import poisson_blend_batch
+        st = lambda xs: np.ascontiguousarray(np.stack(xs, 0))
+        out, unf = poisson_blend_batch(st(trg), st(gx), st(gy), st(hole), st(gmask), device=self.dev)
+        out, unf = out.cpu().numpy(), unf.cpu().numpy()
+        return [(out[i], unf[i]) for i in range(out.shape[0])]
+
+    def fgt_stage(self, frame_blends, mask, flow_f, step, num_ref, neighbor_stride):
+        from .clip import inpaint_clip
+        return inpaint_clip(self.fgt, frame_blends, mask, flow_f, step, num_ref, neighbor_stride, device=self.dev)
+
+
+# ------------------------------------------------------------------------------------------------ driver
+def video_inpainting(frames_u8, masks_u8, backend, args=None, num_flows=3, flow_interval=3, return_stages=False):
+    """Object removal on a clip: frames_u8 [N,h,w,3] RGB uint8 (the PNGs the driver reads), masks_u8 [N,h,w]
+    (non-zero = remove) -> list of N uint8 RGB frames [imgH,imgW,3] (what the driver writes to result.mp4).
+    `args`: make_args(...); num_flows / flow_interval are the LAFC config entries the driver reads (:352)."""
+    args = args or make_args()
+    video, video_flow = load_clip(frames_u8, args)
+    flow_f = compute_flows(backend, video_flow, args, "forward")
+    flow_b = compute_flows(backend, video_flow, args, "backward")
+    video = np.ascontiguousarray(video.permute(2, 3, 1, 0).numpy()[:, :, ::-1, :]) / 255.0       # [H,W,3(BGR),N], :499-501
+    video = video.astype(np.float32)
+    mask, mask_dilated, flow_mask = prepare_masks(masks_u8, args)
+    done_f = complete_flows(backend, flow_f, flow_mask, "forward", num_flows, flow_interval)
+    done_b = complete_flows(backend, flow_b, flow_mask, "backward", num_flows, flow_interval)
+    gx, gy = prepare_gradients(video, mask, mask_dilated)
+    gx, gy, mask_gradient = backend.propagate(args, gx, gy, mask, mask_dilated, done_f, done_b)
+    frame_blends = blend_frames(backend, video, gx, gy, mask, np.array(mask_gradient, dtype=bool))
+    comp = backend.fgt_stage(frame_blends, mask, done_f, args.step, args.num_ref, args.neighbor_stride)
+    if return_stages:
+        return comp, dict(flow_f=flow_f, flow_b=flow_b, done_f=done_f, done_b=done_b, mask_gradient=mask_gradient,
+                          frame_blends=np.stack(frame_blends), mask=mask)
+    return comp

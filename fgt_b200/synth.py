@@ -416,3 +416,23 @@ def poisson_inputs(seed=0, F=3, H=64, W=96, with_edge=False):
     edge = np.zeros((F, H, W), dtype=np.float32)
     edge[:, H // 3, :] = 1.0
     return trg, gx, gy, hole, gm, edge
+
+
+# ----------------------------------------------------------------------------------------------
+# whole driver pipeline (tool/video_inpainting.py::video_inpainting)
+# ----------------------------------------------------------------------------------------------
+def pipeline_clip(seed=5, N=7, H=64, W=96):
+    """What the driver reads from disk: N uint8 RGB frames [H,W,3] (a smooth texture translating by (2, 1) px per
+    frame) and N uint8 masks [H,W] (255 = remove; a box moving with the texture)."""
+    import numpy as np
+    g = torch.Generator().manual_seed(seed)
+    big = _smooth(torch.rand(1, 3, H + 64, W + 64, generator=g), k=7)[0]
+    big = (big - big.amin()) / (big.amax() - big.amin())
+    frames, masks = [], []
+    for i in range(N):
+        y0, x0 = 16 + i, 16 + 2 * i
+        frames.append((big[:, y0:y0 + H, x0:x0 + W].permute(1, 2, 0).numpy() * 255).astype(np.uint8))
+        m = np.zeros((H, W), np.uint8)
+        m[H // 3 + i:H // 3 + H // 4 + i, W // 3 + 2 * i:W // 3 + W // 4 + 2 * i] = 255
+        masks.append(m)
+    return frames, masks

@@ -9,9 +9,11 @@
 
 Only available in the build container (/root/reference). The driver imports three packages that are not in
 this image (cvbase: .flo visualisation, imageio: video writer, skimage.feature.canny: unused in this mode); they
-are stubbed, `imageio.mimwrite` being the hook that captures the final frames. RAFT uses the real
-raft-things.pth; FGT / LAFC checkpoints (not in the repository) are the seeded synthetic weights of
-fgt_b200.synth written to temporary checkpoint directories in the layout `initialize_FGT/LAFC` expects.
+are stubbed, `imageio.mimwrite` being the hook that captures the final frames. All three networks use the
+seeded synthetic weights of fgt_b200.synth (the FGT / LAFC checkpoints are not in the reference repository, and
+the real raft-things.pth cannot travel to the GPU box), written to temporary checkpoint files in the layout
+`initialize_RAFT/LAFC/FGT` expect. Also recorded for stage-wise diagnosis: RAFT flows, completed flows and the
+propagation's mask                                                                                  -> pipeline_stages.npz
 """
 import argparse
 import contextlib
@@ -37,22 +39,6 @@ H, W, N = 64, 96, 7
 CAPTURE = {}
 
 
-def clip_frames(seed=5):
-    """N uint8 RGB frames: a smooth texture translating by (2, 1) px per frame, plus a moving box mask."""
-    g = torch.Generator().manual_seed(seed)
-    big = synth._smooth(torch.rand(1, 3, H + 64, W + 64, generator=g), k=7)[0]
-    big = (big - big.amin()) / (big.amax() - big.amin())
-    frames, masks = [], []
-    for i in range(N):
-        y0, x0 = 16 + i, 16 + 2 * i
-        fr = (big[:, y0:y0 + H, x0:x0 + W].permute(1, 2, 0).numpy() * 255).astype(np.uint8)
-        m = np.zeros((H, W), np.uint8)
-        m[20 + i:38 + i, 30 + 2 * i:52 + 2 * i] = 255
-        frames.append(fr)
-        masks.append(m)
-    return frames, masks
-
-
 def main():
     for m in ("cvbase", "imageio", "skimage", "skimage.feature"):
         sys.modules.setdefault(m, types.ModuleType(m))
@@ -63,7 +49,7 @@ def main():
 
     tmp = tempfile.mkdtemp(prefix="fgt_pipeline_")
     try:
-        frames, masks = clip_frames()
+        frames, masks = synth.pipeline_clip(seed=5, N=N, H=H, W=W)
         for d in ("frames", "masks", "fgt_ckpt", "lafc_ckpt", "out"):
             os.makedirs(os.path.join(tmp, d))
         for i, (fr, m) in enumerate(zip(frames, masks)):
@@ -81,13 +67,15 @@ def main():
         torch.save({"model_state_dict": lafc_sd}, os.path.join(tmp, "lafc_ckpt", "lafc.tar"))
         with open(os.path.join(tmp, "lafc_ckpt", "config.yaml"), "w") as fh:
             yaml.safe_dump(dict(synth.CFG_LAFC), fh)
+        raft_sd = synth.raft_state_dict(seed=33)
+        torch.save({"module." + k: v for k, v in raft_sd.items()}, os.path.join(tmp, "raft.pth"))
         opt = os.path.join(tmp, "opt.yaml")
         with open(opt, "w") as fh:
             yaml.safe_dump(dict(mode="object_removal", consistencyThres=5, alpha=0.1, flow_mask_dilates=3, frame_dilates=1), fh)
         args = argparse.Namespace(
             opt=opt, mode="object_removal", path=os.path.join(tmp, "frames"), path_mask=os.path.join(tmp, "masks"),
             outroot=os.path.join(tmp, "out"), consistencyThres=5.0, alpha=0.1, Nonlocal=False,
-            raft_model=os.path.join(REF, "LAFC", "flowCheckPoint", "raft-things.pth"), small=False, mixed_precision=False,
+            raft_model=os.path.join(tmp, "raft.pth"), small=False, mixed_precision=False,
             alternate_corr=False, lafc_ckpts=os.path.join(tmp, "lafc_ckpt"), fgt_ckpts=os.path.join(tmp, "fgt_ckpt"),
             H_scale=2, W_scale=2, imgH=H, imgW=W, flow_mask_dilates=3, frame_dilates=1, gpu=0, step=10, num_ref=-1,
             neighbor_stride=5, vis_flows=False, vis_completed_flows=False, vis_prop=False, vis_frame=False)
@@ -106,6 +94,25 @@ def main():
             p_calls.append(([np.array(x) for x in a], [np.array(o) for o in out]))
             return out
 
+        stages = {}
+        ref_calc, ref_comp, ref_prop = VI.calculate_flow, VI.complete_flow, VI.get_flowNN_gradient
+
+        def calc(a, model, video, mode):
+            out = ref_calc(a, model, video, mode)
+            stages["flow_" + mode[0]] = np.array(out)
+            return out
+
+        def comp_flow(config, model, flows, masks, mode, device):
+            out = ref_comp(config, model, flows, masks, mode, device)
+            stages["done_" + mode[0]] = VI.tensor2np(out)
+            return out
+
+        def prop(*a):
+            out = ref_prop(*a)
+            stages["mask_gradient"] = np.array(out[2])
+            return out
+
+        VI.calculate_flow, VI.complete_flow, VI.get_flowNN_gradient = calc, comp_flow, prop
         VI.np2tensor, VI.Poisson_blend_img = np2tensor, poisson
         with contextlib.redirect_stdout(io.StringIO()):
             VI.video_inpainting(args)
@@ -114,7 +121,7 @@ def main():
 
     import cv2
     import scipy
-    meta = dict(H=H, W=W, N=N, fgt_seed=31, lafc_seed=32, torch=torch.__version__, numpy=np.__version__,
+    meta = dict(H=H, W=W, N=N, fgt_seed=31, lafc_seed=32, raft_seed=33, clip_seed=5, flow_mask_dilates=3, frame_dilates=1, torch=torch.__version__, numpy=np.__version__,
                 scipy=scipy.__version__, cv2=cv2.__version__)
     frame_blends, mask, flow_f = t_calls            # the three near="t" conversions of the FGT stage, in order
     comp = np.stack(CAPTURE["comp_frames"])
@@ -130,6 +137,11 @@ def main():
     assert trg.dtype in (np.float32, np.float64) and gx.dtype == np.float32 and hole.dtype == np.bool_
     np.savez_compressed(os.path.join(HERE, "pipeline_poisson.npz"), meta=np.array(repr(meta)), trg=trg, gx=gx, gy=gy,
                         hole=np.packbits(hole), gmask=np.packbits(gm), blend_hole=blend[hole], unfilled=np.packbits(unf))
+    np.savez_compressed(os.path.join(HERE, "pipeline_stages.npz"), meta=np.array(repr(meta)),
+                        flow_f=stages["flow_f"].astype(np.float16), flow_b=stages["flow_b"].astype(np.float16),
+                        done_f=stages["done_f"].astype(np.float16), done_b=stages["done_b"].astype(np.float16),
+                        mask_gradient=np.packbits(stages["mask_gradient"]))
+    print("flow magnitudes: raw", np.abs(stages["flow_f"]).mean(), "completed", np.abs(stages["done_f"]).mean())
     print("pipeline goldens saved:", len(p_calls), "Poisson calls, holes", int(hole.sum()), "unfilled", int(unf.sum()),
           "| comp mean", comp.mean(), "| blend dtype", blend.dtype, "trg dtype", trg.dtype)
 
