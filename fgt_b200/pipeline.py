@@ -69,7 +69,7 @@ def compute_flows(backend, video_flow, args, mode):
     working resolution with the flow vectors rescaled. Returns [imgH,imgW,2,N-1] float32."""
     a, b = (video_flow[:-1], video_flow[1:]) if mode == "forward" else (video_flow[1:], video_flow[:-1])
     flows = backend.raft_pairs(a, b, args.raft_iters)                   # [N-1,2,h,w]
-    out = np.empty((args.imgH, args.imgW, 2, 0), dtype=np.float32)
+    out = np.empty((args.imgH, args.imgW, 2, flows.shape[0]), dtype=np.float32)   # (the driver grows it by concatenation)
     for i in range(flows.shape[0]):
         flow = np.ascontiguousarray(flows[i].transpose(1, 2, 0))
         h, w = flow.shape[:2]
@@ -77,7 +77,7 @@ def compute_flows(backend, video_flow, args, mode):
             flow = cv2.resize(flow, (args.imgW, args.imgH), cv2.INTER_LINEAR)   # same positional call as the driver
             flow[:, :, 0] *= float(args.imgW) / float(w)
             flow[:, :, 1] *= float(args.imgH) / float(h)
-        out = np.concatenate((out, flow[..., None]), axis=-1)
+        out[..., i] = flow
     return out
 
 
@@ -114,16 +114,14 @@ def prepare_gradients(video, mask, mask_dilated):
     """:583-614 — zero the hole (in place, like the driver), TELEA-inpaint it for a plausible initialisation, take
     forward differences and zero them wherever they touch the hole. video [H,W,3,N] float32 (BGR, 0..1)."""
     H, W, _, N = video.shape
-    gx = np.empty((H, W, 3, 0), dtype=np.float32)
-    gy = np.empty((H, W, 3, 0), dtype=np.float32)
+    gx = np.zeros((H, W, 3, N), dtype=np.float32)      # last column / row stay zero (:601-606)
+    gy = np.zeros((H, W, 3, N), dtype=np.float32)
     for i in range(N):
         img = video[:, :, :, i]
         img[mask[:, :, i], :] = 0
         img = cv2.inpaint((img * 255).astype(np.uint8), mask[:, :, i].astype(np.uint8), 3, cv2.INPAINT_TELEA).astype(np.float32) / 255.0
-        dx = np.concatenate((np.diff(img, axis=1), np.zeros((H, 1, 3), dtype=np.float32)), axis=1)
-        dy = np.concatenate((np.diff(img, axis=0), np.zeros((1, W, 3), dtype=np.float32)), axis=0)
-        gx = np.concatenate((gx, dx.reshape(H, W, 3, 1)), axis=-1)
-        gy = np.concatenate((gy, dy.reshape(H, W, 3, 1)), axis=-1)
+        gx[:, :W - 1, :, i] = np.diff(img, axis=1)
+        gy[:H - 1, :, :, i] = np.diff(img, axis=0)
         gx[mask_dilated[:, :, i], :, i] = 0
         gy[mask_dilated[:, :, i], :, i] = 0
     return gx, gy
