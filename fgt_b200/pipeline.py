@@ -230,3 +230,68 @@ def video_inpainting(frames_u8, masks_u8, backend, args=None, num_flows=3, flow_
         return comp, dict(flow_f=flow_f, flow_b=flow_b, done_f=done_f, done_b=done_b, mask_gradient=mask_gradient,
                           frame_blends=np.stack(frame_blends), mask=mask)
     return comp
+
+
+# ------------------------------------------------------------------------------------------------ command line
+def load_models(raft_model, lafc_ckpts, fgt_ckpts, device):
+    """initialize_RAFT / initialize_LAFC / initialize_FGT (:186-230) with the drop-in modules: the same checkpoint
+    layout (a `module.`-prefixed RAFT state dict; directories holding one *.tar with `model_state_dict` and one
+    *.yaml config). Returns (GpuBackend, lafc_config)."""
+    import glob
+    import os
+
+    import yaml
+
+    from .fgt_model import Model as FGTModel
+    from .lafc_model import Model as LAFCModel
+    from .raft_model import RAFT
+
+    def ckpt_dir(d):
+        tars, yamls = glob.glob(os.path.join(d, "*.tar")), glob.glob(os.path.join(d, "*.yaml"))
+        if len(tars) != 1 or len(yamls) != 1:
+            raise FileNotFoundError(f"{d}: expected exactly one *.tar and one *.yaml (found {len(tars)}, {len(yamls)})")
+        with open(yamls[0]) as fh:
+            return torch.load(tars[0], map_location="cpu")["model_state_dict"], yaml.full_load(fh)
+
+    raft = torch.nn.DataParallel(RAFT(argparse.Namespace(small=False, mixed_precision=False, alternate_corr=False)))
+    raft.load_state_dict(torch.load(raft_model, map_location="cpu"))
+    raft = raft.module.to(device).eval()
+    lafc_sd, lafc_cfg = ckpt_dir(lafc_ckpts)
+    lafc = LAFCModel(lafc_cfg)
+    lafc.load_state_dict(lafc_sd)
+    fgt_sd, fgt_cfg = ckpt_dir(fgt_ckpts)
+    fgt = FGTModel(fgt_cfg)
+    fgt.load_state_dict(fgt_sd)
+    return GpuBackend(raft, lafc.to(device), fgt.to(device), device=device), lafc_cfg
+
+
+def main(argv=None):
+    """`python -m fgt_b200.pipeline --path frames/ --path_mask masks/ --outroot out/ ...` — the driver's command line
+    for object removal (:764-855; options of the other modes and the visualisation switches are not offered)."""
+    from . import io as IO
+    ap = argparse.ArgumentParser(description=main.__doc__)
+    ap.add_argument("--path", required=True, help="directory of *.png / *.jpg frames")
+    ap.add_argument("--path_mask", required=True, help="directory of masks (non-zero = remove)")
+    ap.add_argument("--outroot", required=True, help="output directory (frames/%%05d.png, result.mp4)")
+    ap.add_argument("--raft_model", default="../LAFC/flowCheckPoint/raft-things.pth")
+    ap.add_argument("--lafc_ckpts", default="../LAFC/checkpoint")
+    ap.add_argument("--fgt_ckpts", default="../FGT/checkpoint")
+    ap.add_argument("--gpu", type=int, default=0)
+    for k, v in DEFAULTS.items():
+        if k not in ("Nonlocal", "raft_iters"):
+            ap.add_argument("--" + k, type=type(v), default=v)
+    ns = ap.parse_args(argv)
+    dev = torch.device("cuda", ns.gpu)
+    backend, lafc_cfg = load_models(ns.raft_model, ns.lafc_ckpts, ns.fgt_ckpts, dev)
+    args = make_args(**{k: getattr(ns, k) for k in DEFAULTS if hasattr(ns, k)})
+    frames, masks = IO.read_frames(ns.path), IO.read_masks(ns.path_mask)
+    if len(frames) != len(masks):
+        raise ValueError(f"{len(frames)} frames but {len(masks)} masks")
+    comp = video_inpainting(frames, masks, backend, args, lafc_cfg["num_flows"], lafc_cfg["flow_interval"])
+    written = IO.write_frames(ns.outroot, comp)
+    print(f"Done, {len(comp)} frames written to {ns.outroot} ({len(written)} files)")
+    return comp
+
+
+if __name__ == "__main__":
+    main()

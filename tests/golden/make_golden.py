@@ -219,6 +219,13 @@ def poisson_case(name, F, H, W, seed, with_edge):
 
 
 if __name__ == "__main__":
+    if "--flo-only" in sys.argv:       # 3x5 flow written by the reference's writer (tests/test_io.py)
+        sys.path.insert(0, os.path.join(REF, "RAFT"))
+        from utils import frame_utils as FU
+        from tests.test_io import _flow
+        FU.writeFlow(os.path.join(HERE, "flo_ref.flo"), _flow())
+        assert np.array_equal(FU.readFlow(os.path.join(HERE, "flo_ref.flo")), _flow())
+        sys.exit(0)
     if "--poisson-only" in sys.argv:
         poisson_case("poisson_small", 3, 64, 96, seed=7, with_edge=False)
         poisson_case("poisson_edge", 2, 48, 64, seed=8, with_edge=True)

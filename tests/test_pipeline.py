@@ -9,6 +9,8 @@ Goldens (tests/golden/pipeline_*.npz) come from ONE RUN OF THE UNMODIFIED REFERE
   synthetic weights, hard consistency thresholds in the propagation), so 1e-4-level differences of the CUDA networks can
   move individual pixels across a threshold; the test therefore checks the stage outputs statistically (stated per
   assertion) and the final frames by mean absolute error and the fraction of values off by more than 2 levels."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -97,3 +99,44 @@ def test_gpu_pipeline_vs_reference_driver():
         assert rep[k][0] < 2e-3 * rep[k][2] and rep[k][1] < 1e-2 * rep[k][2], (k, rep[k])
     assert rep["mask_gradient_mismatch"] < 1e-3, rep
     assert rep["comp"][0] < 0.05 and rep["comp"][1] <= 8 and rep["comp"][2] < 1e-3, rep
+
+
+def _write_ckpts(tmp, cfg, sds):
+    import yaml
+    os.makedirs(os.path.join(tmp, "fgt")); os.makedirs(os.path.join(tmp, "lafc"))
+    torch.save({"model_state_dict": sds["fgt"]}, os.path.join(tmp, "fgt", "fgt.tar"))
+    with open(os.path.join(tmp, "fgt", "config.yaml"), "w") as fh:
+        yaml.safe_dump({**{k: (list(v) if isinstance(v, tuple) else v) for k, v in cfg.items()}, "model": "model"}, fh)
+    torch.save({"model_state_dict": sds["lafc"]}, os.path.join(tmp, "lafc", "lafc.tar"))
+    with open(os.path.join(tmp, "lafc", "config.yaml"), "w") as fh:
+        yaml.safe_dump(dict(synth.CFG_LAFC), fh)
+    torch.save({"module." + k: v for k, v in sds["raft"].items()}, os.path.join(tmp, "raft.pth"))
+
+
+def test_cli_argument_and_checkpoint_errors(tmp_path):
+    with pytest.raises(SystemExit):
+        PL.main(["--path", "x"])                                        # required options missing
+    os.makedirs(tmp_path / "empty")
+    with pytest.raises(FileNotFoundError):
+        PL.load_models(str(tmp_path / "nope.pth"), str(tmp_path / "empty"), str(tmp_path / "empty"), "cpu")
+
+
+@pytest.mark.gpu
+def test_gpu_command_line_end_to_end(tmp_path):
+    """The driver's command line on directories of PNGs with checkpoints in the driver's layout; same frames as the
+    array entry point (and therefore as the reference driver's golden)."""
+    from fgt_b200 import io as IO
+    g, st, frames, masks, args, cfg, sds = _setup()
+    tmp = str(tmp_path)
+    _write_ckpts(tmp, cfg, sds)
+    IO.write_frames(os.path.join(tmp, "in"), frames, mp4=False)
+    IO.write_frames(os.path.join(tmp, "msk"), [np.repeat(m[..., None], 3, -1) for m in masks], mp4=False)
+    comp = PL.main(["--path", os.path.join(tmp, "in", "frames"), "--path_mask", os.path.join(tmp, "msk", "frames"),
+                    "--outroot", os.path.join(tmp, "out"), "--raft_model", os.path.join(tmp, "raft.pth"),
+                    "--lafc_ckpts", os.path.join(tmp, "lafc"), "--fgt_ckpts", os.path.join(tmp, "fgt"),
+                    "--imgH", str(args.imgH), "--imgW", str(args.imgW), "--flow_mask_dilates", str(args.flow_mask_dilates),
+                    "--frame_dilates", str(args.frame_dilates)])
+    back = IO.read_frames(os.path.join(tmp, "out", "frames"))
+    assert len(back) == len(frames) and all(np.array_equal(a, b) for a, b in zip(back, comp))
+    diff = np.abs(np.stack(comp).astype(np.int16) - g["comp"].astype(np.int16))
+    assert diff.max() <= 8 and diff.mean() < 0.05
