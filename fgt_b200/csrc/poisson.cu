@@ -18,7 +18,8 @@
 //                     x += t1 w, w = v + t2 w,                      ww[k+1] += |w|^2
 //                     u^ = A v - alfa_k * u,                        bb[k+1] += |u^|^2 (beta_{k+1}^2)
 // Per-iteration sums live in zero-initialised slot arrays indexed by iteration, so nothing is ever reset, and a
-// system that has stopped (its own istop) is frozen while the others continue. HBM/L2-bound fp64 streaming.
+// system that has stopped (its own istop) is frozen while the others continue. The iteration index is a device
+// counter, so a chunk of iterations is captured once as a CUDA graph and replayed. HBM/L2-bound fp64 streaming.
 #include "common.h"
 
 #include <math.h>
@@ -188,7 +189,7 @@ __global__ void psn_setup_kernel(const double* __restrict__ trg, const double* _
                                  const double* __restrict__ gy, const unsigned char* __restrict__ hole,
                                  const unsigned char* __restrict__ gmask, const unsigned char* __restrict__ edge, int H,
                                  int W, int S, unsigned char* __restrict__ code, double* __restrict__ u,
-                                 double* __restrict__ bb, int* __restrict__ list, int* __restrict__ cnt) {
+                                 double* __restrict__ bb, unsigned* __restrict__ list, int* __restrict__ cnt) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ double red[kPsnC][kPsnThreads / 32];
@@ -198,8 +199,8 @@ __global__ void psn_setup_kernel(const double* __restrict__ trg, const double* _
   const int i = blockIdx.x * kPsnThreads + threadIdx.x;
   double acc[kPsnC] = {0.0, 0.0, 0.0};
   bool owns = false;
+  unsigned cd = 0;
   if (i < HW) {
-    unsigned cd = 0;
     if (hole[fb + i]) {
       const int y = i / W, x = i - y * W;
       const bool e_p = edge && edge[fb + i];
@@ -245,7 +246,7 @@ __global__ void psn_setup_kernel(const double* __restrict__ trg, const double* _
       s_base = tot ? atomicAdd(&cnt[f], tot) : 0;
     }
     __syncthreads();
-    if (owns) list[fb + s_base + s_woff[warp] + __popc(bal & ((1u << lane) - 1u))] = i;
+    if (owns) list[fb + s_base + s_woff[warp] + __popc(bal & ((1u << lane) - 1u))] = static_cast<unsigned>(i) | (cd << 24);
     __syncthreads();
   }
   psn_block_sum(acc, red);
@@ -254,16 +255,24 @@ __global__ void psn_setup_kernel(const double* __restrict__ trg, const double* _
       if (acc[c] != 0.0) atomicAdd(&bb[f * kPsnC + c], acc[c]);
 }
 
-__global__ void psn_v_kernel(const unsigned char* __restrict__ code, const int* __restrict__ list,
-                             const int* __restrict__ cnt, int H, int W, int S, const double* __restrict__ u,
+// Iteration kernels. The iteration index lives on the device (kctr[0]: read by psn_v, written by psn_ux; kctr[1]:
+// read by psn_ux, written by psn_v — no kernel reads a word it writes), so the launch sequence has no changing
+// parameter and a chunk of iterations replays as ONE CUDA graph. A list entry packs the pixel index (low 24 bits)
+// and its equation code (high 8 bits); entries past a frame's count are 0 = "no equation".
+__global__ void psn_v_kernel(const unsigned* __restrict__ list, int H, int W, int S, const double* __restrict__ u,
                              double* __restrict__ v, const double* __restrict__ bb, double* __restrict__ aa,
-                             const double* __restrict__ state, int k) {
+                             const double* __restrict__ state, int* __restrict__ kctr) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ double red[kPsnC][kPsnThreads / 32];
   __shared__ double s_inv[kPsnC], s_coef[kPsnC];
   __shared__ int s_act[kPsnC];
   const int f = blockIdx.y, HW = H * W;
+  const int k = kctr[0];
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) kctr[1] = k;
+  const long long fb = static_cast<long long>(f) * HW;
+  const int j = blockIdx.x * kPsnThreads + threadIdx.x;
+  const unsigned entry = j < HW ? list[fb + j] : 0u;      // issued before the scalar prologue
   if (threadIdx.x < kPsnC) {
     const int s = f * kPsnC + threadIdx.x;
     const double* st = state + (static_cast<long long>((k + 1) & 1) * S + s) * kPsnState;   // parity of k-1
@@ -274,14 +283,11 @@ __global__ void psn_v_kernel(const unsigned char* __restrict__ code, const int* 
     s_inv[threadIdx.x] = act ? 1.0 / beta : 0.0;
     s_coef[threadIdx.x] = (act && k >= 1) ? beta * st[PS_VSCALE] : 0.0;
   }
-  __syncthreads();
-  const long long fb = static_cast<long long>(f) * HW;
-  const int j = blockIdx.x * kPsnThreads + threadIdx.x;
-  const int i = j < cnt[f] ? list[fb + j] : -1;
+  const unsigned cd = entry >> 24;
+  const int i = static_cast<int>(entry & 0xffffffu);
   double acc[kPsnC] = {0.0, 0.0, 0.0};
-  const unsigned cd = i >= 0 ? code[fb + i] : 0u;
+  double s[kPsnC] = {0.0, 0.0, 0.0}, vo[kPsnC] = {0.0, 0.0, 0.0};
   if (cd & 15u) {
-    double s[kPsnC] = {0.0, 0.0, 0.0};
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
       if (!((cd >> n) & 1u)) continue;
@@ -294,11 +300,16 @@ __global__ void psn_v_kernel(const unsigned char* __restrict__ code, const int* 
         for (int c = 0; c < kPsnC; ++c) s[c] -= uq[c];
       }
     }
+#pragma unroll
+    for (int c = 0; c < kPsnC; ++c) vo[c] = v[(fb + i) * kPsnC + c];
+  }
+  __syncthreads();
+  if (cd & 15u) {
     double* vp = v + (fb + i) * kPsnC;
 #pragma unroll
     for (int c = 0; c < kPsnC; ++c) {
       if (!s_act[c]) continue;
-      const double nv = s[c] * s_inv[c] - s_coef[c] * vp[c];
+      const double nv = s[c] * s_inv[c] - s_coef[c] * vo[c];
       vp[c] = nv;
       acc[c] = nv * nv;
     }
@@ -309,16 +320,45 @@ __global__ void psn_v_kernel(const unsigned char* __restrict__ code, const int* 
       if (acc[c] != 0.0) atomicAdd(&aa[static_cast<long long>(k) * S + f * kPsnC + c], acc[c]);
 }
 
-__global__ void psn_ux_kernel(const unsigned char* __restrict__ code, const int* __restrict__ list,
-                              const int* __restrict__ cnt, int H, int W, int S, double* __restrict__ u,
+__global__ void psn_ux_kernel(const unsigned* __restrict__ list, int H, int W, int S, double* __restrict__ u,
                               const double* __restrict__ v, double* __restrict__ w, double* __restrict__ x,
                               double* __restrict__ bb, const double* __restrict__ aa, double* __restrict__ ww,
-                              double* __restrict__ state, int k, double atol, double btol, double ctol, int iter_lim) {
+                              double* __restrict__ state, int* __restrict__ kctr, double atol, double btol, double ctol,
+                              int iter_lim) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ double red[kPsnC][kPsnThreads / 32];
   __shared__ PsnStep s_step[kPsnC];
   const int f = blockIdx.y, HW = H * W;
+  const int k = kctr[1];
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) kctr[0] = k + 1;
+  const long long fb = static_cast<long long>(f) * HW;
+  const int j = blockIdx.x * kPsnThreads + threadIdx.x;
+  const unsigned entry = j < HW ? list[fb + j] : 0u;
+  const unsigned cd = entry >> 24;
+  const int i = static_cast<int>(entry & 0xffffffu);
+  // the u / v operands (27 of this thread's 33 loads) are issued before the barrier, i.e. while threads 0..2 run
+  // the scalar recurrence; w and x are touched after it
+  double vown[kPsnC] = {0.0, 0.0, 0.0};
+  double uo[4][kPsnC], vq[4][kPsnC];
+#pragma unroll
+  for (int n = 0; n < 4; ++n)
+#pragma unroll
+    for (int c = 0; c < kPsnC; ++c) uo[n][c] = vq[n][c] = 0.0;
+  if (cd & 15u) {
+#pragma unroll
+    for (int c = 0; c < kPsnC; ++c) vown[c] = v[(fb + i) * kPsnC + c];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      if (!((cd >> n) & 1u)) continue;
+#pragma unroll
+      for (int c = 0; c < kPsnC; ++c) uo[n][c] = u[((static_cast<long long>(f) * 4 + n) * HW + i) * kPsnC + c];
+      if ((cd >> (4 + n)) & 1u) {
+#pragma unroll
+        for (int c = 0; c < kPsnC; ++c) vq[n][c] = v[(fb + i + psn_nb(n, W)) * kPsnC + c];
+      }
+    }
+  }
   if (threadIdx.x < kPsnC) {
     const int s = f * kPsnC + threadIdx.x;
     const double* prev = state + (static_cast<long long>((k + 1) & 1) * S + s) * kPsnState;
@@ -329,44 +369,34 @@ __global__ void psn_ux_kernel(const unsigned char* __restrict__ code, const int*
     s_step[threadIdx.x] = st;
     if (blockIdx.x == 0) {
       double* dst = state + (static_cast<long long>(k & 1) * S + s) * kPsnState;
-      for (int j = 0; j < kPsnState; ++j) dst[j] = cur[j];
+      for (int q = 0; q < kPsnState; ++q) dst[q] = cur[q];
     }
   }
   __syncthreads();
-  const long long fb = static_cast<long long>(f) * HW;
-  const int j = blockIdx.x * kPsnThreads + threadIdx.x;
-  const int i = j < cnt[f] ? list[fb + j] : -1;
   double accw[kPsnC] = {0.0, 0.0, 0.0}, accu[kPsnC] = {0.0, 0.0, 0.0};
-  const unsigned cd = i >= 0 ? code[fb + i] : 0u;
   if (cd & 15u) {
-    const double* vp = v + (fb + i) * kPsnC;
-    double* wp = w + (fb + i) * kPsnC;
-    double* xp = x + (fb + i) * kPsnC;
     double vn[kPsnC];
 #pragma unroll
     for (int c = 0; c < kPsnC; ++c) {
       const PsnStep& st = s_step[c];
-      vn[c] = vp[c] * st.vscale;
+      vn[c] = vown[c] * st.vscale;
       if (st.skip_all) continue;
-      const double wo = wp[c];
-      xp[c] += st.t1 * wo;
+      const double wo = w[(fb + i) * kPsnC + c];
+      x[(fb + i) * kPsnC + c] += st.t1 * wo;
       const double wn = vn[c] + st.t2 * wo;
-      wp[c] = wn;
+      w[(fb + i) * kPsnC + c] = wn;
       accw[c] = wn * wn;
     }
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
       if (!((cd >> n) & 1u)) continue;
-      double* up = u + ((static_cast<long long>(f) * 4 + n) * HW + i) * kPsnC;
-      const bool inh = (cd >> (4 + n)) & 1u;
-      const double* vq = v + (fb + i + psn_nb(n, W)) * kPsnC;
 #pragma unroll
       for (int c = 0; c < kPsnC; ++c) {
         const PsnStep& st = s_step[c];
         if (st.skip_u) continue;
-        const double av = vn[c] - (inh ? vq[c] * st.vscale : 0.0);
-        const double nu = av - st.au * up[c];
-        up[c] = nu;
+        const double av = vn[c] - vq[n][c] * st.vscale;   // vq is 0 when the neighbour lies outside the hole
+        const double nu = av - st.au * uo[n][c];
+        u[((static_cast<long long>(f) * 4 + n) * HW + i) * kPsnC + c] = nu;
         accu[c] += nu * nu;
       }
     }
@@ -454,36 +484,82 @@ static dim3 psn_grid(int F, int H, int W) { return dim3((H * W + kPsnThreads - 1
 
 extern "C" int fgt_poisson_setup(const double* trg, const double* gx, const double* gy, const unsigned char* hole,
                                  const unsigned char* gmask, const unsigned char* edge, int F, int H, int W,
-                                 unsigned char* code, double* u, double* bb, int* list, int* cnt,
+                                 unsigned char* code, double* u, double* bb, unsigned* list, int* cnt,
                                  fgt_stream_t stream) {
   FGT_REQUIRE(trg && gx && gy && hole && code && u && bb && list && cnt && F >= 1 && H >= 2 && W >= 2, FGT_ERR_ARG,
               "poisson_setup: bad argument");
+  FGT_REQUIRE(static_cast<long long>(H) * W < (1LL << 24), FGT_ERR_ARG, "poisson_setup: H*W must be below 2^24");
   launch_k(psn_setup_kernel, psn_grid(F, H, W), dim3(kPsnThreads), 0, reinterpret_cast<cudaStream_t>(stream), trg, gx,
            gy, hole, gmask, edge, H, W, F * kPsnC, code, u, bb, list, cnt);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;
 }
 
-extern "C" int fgt_poisson_iters(const unsigned char* code, const int* list, const int* cnt, int max_cnt, int F, int H,
-                                 int W, double* u, double* v, double* w, double* x, double* bb, double* aa, double* ww,
-                                 double* state, int k0, int iters, double atol, double btol, double conlim,
-                                 int iter_lim, fgt_stream_t stream) {
-  FGT_REQUIRE(code && list && cnt && u && v && w && x && bb && aa && ww && state && F >= 1 && k0 >= 0 && iters >= 1 &&
-                  max_cnt >= 0 && max_cnt <= H * W,
-              FGT_ERR_ARG, "poisson_iters: bad argument");
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+static int psn_enqueue(const unsigned* list, int max_cnt, int F, int H, int W, double* u, double* v, double* w, double* x,
+                       double* bb, double* aa, double* ww, double* state, int* kctr, int iters, double atol, double btol,
+                       double conlim, int iter_lim, cudaStream_t st) {
   // one block column even when no pixel owns an equation: block 0 of every frame carries the scalar state
   const dim3 grid(max_cnt > 0 ? (max_cnt + kPsnThreads - 1) / kPsnThreads : 1, F);
   const int S = F * kPsnC;
   const double ctol = conlim > 0.0 ? 1.0 / conlim : 0.0;
-  for (int k = k0; k < k0 + iters; ++k) {
-    launch_k(psn_v_kernel, grid, dim3(kPsnThreads), 0, st, code, list, cnt, H, W, S, static_cast<const double*>(u), v,
-             static_cast<const double*>(bb), aa, static_cast<const double*>(state), k);
-    launch_k(psn_ux_kernel, grid, dim3(kPsnThreads), 0, st, code, list, cnt, H, W, S, u, static_cast<const double*>(v), w, x,
-             bb,
-             static_cast<const double*>(aa), ww, state, k, atol, btol, ctol, iter_lim);
+  for (int it = 0; it < iters; ++it) {
+    FGT_CUDA(launch_k(psn_v_kernel, grid, dim3(kPsnThreads), 0, st, list, H, W, S, static_cast<const double*>(u), v,
+                      static_cast<const double*>(bb), aa, static_cast<const double*>(state), kctr));
+    FGT_CUDA(launch_k(psn_ux_kernel, grid, dim3(kPsnThreads), 0, st, list, H, W, S, u, static_cast<const double*>(v), w, x,
+                      bb, static_cast<const double*>(aa), ww, state, kctr, atol, btol, ctol, iter_lim));
   }
+  return FGT_OK;
+}
+
+#define PSN_ITER_ARGS_OK                                                                                              \
+  (list && u && v && w && x && bb && aa && ww && state && kctr && F >= 1 && iters >= 1 && max_cnt >= 0 && max_cnt <= H * W)
+
+extern "C" int fgt_poisson_iters(const unsigned* list, int max_cnt, int F, int H, int W, double* u, double* v, double* w,
+                                 double* x, double* bb, double* aa, double* ww, double* state, int* kctr, int iters,
+                                 double atol, double btol, double conlim, int iter_lim, fgt_stream_t stream) {
+  FGT_REQUIRE(PSN_ITER_ARGS_OK, FGT_ERR_ARG, "poisson_iters: bad argument");
+  const int rc = psn_enqueue(list, max_cnt, F, H, W, u, v, w, x, bb, aa, ww, state, kctr, iters, atol, btol, conlim,
+                             iter_lim, reinterpret_cast<cudaStream_t>(stream));
+  if (rc != FGT_OK) return rc;
   FGT_CUDA(cudaGetLastError());
+  return FGT_OK;
+}
+
+// The same `iters` iteration pairs captured once into an executable CUDA graph (the iteration index is on the
+// device, so every replay continues where the previous one stopped).
+extern "C" int fgt_poisson_graph_create(const unsigned* list, int max_cnt, int F, int H, int W, double* u, double* v,
+                                        double* w, double* x, double* bb, double* aa, double* ww, double* state,
+                                        int* kctr, int iters, double atol, double btol, double conlim, int iter_lim,
+                                        void** exec_out) {
+  FGT_REQUIRE(PSN_ITER_ARGS_OK && exec_out, FGT_ERR_ARG, "poisson_graph_create: bad argument");
+  *exec_out = nullptr;
+  cudaStream_t cs;
+  FGT_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  int rc = FGT_OK;
+  cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+  if (e == cudaSuccess) {
+    rc = psn_enqueue(list, max_cnt, F, H, W, u, v, w, x, bb, aa, ww, state, kctr, iters, atol, btol, conlim, iter_lim, cs);
+    e = cudaStreamEndCapture(cs, &graph);   // always end the capture, also after a failed launch
+    if (rc == FGT_OK && e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
+  }
+  if (graph) cudaGraphDestroy(graph);
+  cudaStreamDestroy(cs);
+  if (rc != FGT_OK) return rc;
+  if (e != cudaSuccess) return set_err(FGT_ERR_CUDA, "poisson_graph_create: %s", cudaGetErrorString(e));
+  *exec_out = exec;
+  return FGT_OK;
+}
+
+extern "C" int fgt_poisson_graph_launch(void* exec, fgt_stream_t stream) {
+  FGT_REQUIRE(exec, FGT_ERR_ARG, "poisson_graph_launch: null graph");
+  FGT_CUDA(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(exec), reinterpret_cast<cudaStream_t>(stream)));
+  return FGT_OK;
+}
+
+extern "C" int fgt_poisson_graph_destroy(void* exec) {
+  if (exec) FGT_CUDA(cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(exec)));
   return FGT_OK;
 }
 

@@ -93,12 +93,16 @@ def load():
     for fn in (lib.fgt_regionfill_init, lib.fgt_regionfill_iters, lib.fgt_regionfill_finish):
         fn.restype = ctypes.c_int
     lib.fgt_poisson_setup.argtypes = [_c_p] * 6 + [ci, ci, ci, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p]
-    lib.fgt_poisson_iters.argtypes = [_c_p, _c_p, _c_p, ci, ci, ci, ci] + [_c_p] * 8 + [ci, ci, cd_, cd_, cd_, ci, _c_p]
+    lib.fgt_poisson_iters.argtypes = [_c_p, ci, ci, ci, ci] + [_c_p] * 9 + [ci, cd_, cd_, cd_, ci, _c_p]
+    lib.fgt_poisson_graph_create.argtypes = [_c_p, ci, ci, ci, ci] + [_c_p] * 9 + [ci, cd_, cd_, cd_, ci, ctypes.POINTER(ctypes.c_void_p)]
+    lib.fgt_poisson_graph_launch.argtypes = [_c_p, _c_p]
+    lib.fgt_poisson_graph_destroy.argtypes = [_c_p]
     lib.fgt_poisson_unfilled.argtypes = [_c_p, _c_p, ci, ci, ci, _c_p, _c_p]
     lib.fgt_poisson_finish.argtypes = [_c_p, _c_p, _c_p, ci, ci, ci, _c_p, _c_p, _c_p, _c_p]
     lib.fgt_poisson_advance_host.argtypes = [_c_p, _c_p, _c_p, ci, cd_, cd_, cd_, cd_, cd_, cd_, ci]
     for fn in (lib.fgt_poisson_setup, lib.fgt_poisson_iters, lib.fgt_poisson_unfilled, lib.fgt_poisson_finish,
-               lib.fgt_poisson_advance_host):
+               lib.fgt_poisson_advance_host, lib.fgt_poisson_graph_create, lib.fgt_poisson_graph_launch,
+               lib.fgt_poisson_graph_destroy):
         fn.restype = ctypes.c_int
     lib.fgt_plane_max.argtypes = [_c_p, ci, cll, _c_p, _c_p]
     lib.fgt_window_gather.argtypes = [_c_p, _c_p, _c_p, _c_p, _c_p, ci, ci, ci, _c_p, _c_p, _c_p, _c_p]

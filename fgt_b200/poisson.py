@@ -6,12 +6,14 @@ is the LSQR iterate at which the default stopping rule (atol = btol = 1e-6) fire
 rather than replaced by a tighter solve; results agree with the reference to ~1e-6 on [0,1] images (the
 reference's own bidiagonalisation runs in float32). There is no CPU fallback.
 """
+import ctypes
+
 import numpy as np
 import torch
 
 from . import lib
 
-CHUNK = 48            # iterations between convergence checks (one host sync each)
+CHUNK = 48            # iterations per graph replay = between convergence checks (one host sync each)
 MAX_ITERS = 20000     # cap on the slot arrays; the reference's own limit is 2*H*W
 
 
@@ -36,10 +38,11 @@ def _ptr(t):
 
 
 def poisson_blend_batch(trg, gx, gy, hole, gmask=None, edge=None, device=None, return_info=False,
-                        atol=1e-6, btol=1e-6, conlim=1e8, max_iters=MAX_ITERS):
+                        atol=1e-6, btol=1e-6, conlim=1e8, max_iters=MAX_ITERS, use_graph=True):
     """trg [F,H,W,3], gx [F,H,W-1,3], gy [F,H-1,W,3] (forward differences of the source), hole [F,H,W],
     optional gmask / edge [F,H,W] -> (blend float64 [F,H,W,3], UnfilledMask bool [F,H,W]) on the device
-    (+ per-system (istop, itn) int tensors [F,3] with return_info)."""
+    (+ per-system (istop, itn) int tensors [F,3] with return_info). use_graph: replay each chunk of iterations as one
+    CUDA graph (default) or launch its kernels one by one."""
     dev = _dev(device)
     t64 = lambda a: torch.as_tensor(np.ascontiguousarray(a) if not torch.is_tensor(a) else a).to(dev, torch.float64).contiguous()
     trg, gx, gy = t64(trg), t64(gx), t64(gy)
@@ -59,10 +62,12 @@ def poisson_blend_batch(trg, gx, gy, hole, gmask=None, edge=None, device=None, r
     code = torch.zeros(F, H, W, dtype=torch.uint8, device=dev)
     u = z64(F, 4, H * W, C)
     v, w, x = z64(F, H * W, C), z64(F, H * W, C), z64(F, H * W, C)
-    bb, aa, ww = z64((max_iters + 2) * S), z64((max_iters + 2) * S), z64((max_iters + 2) * S)
+    slots = max_iters + CHUNK + 2                      # a replay may run past the last stop by < CHUNK (frozen) iterations
+    bb, aa, ww = z64(slots * S), z64(slots * S), z64(slots * S)
     state = z64(2, S, 16)
-    plist = torch.empty(F, H * W, dtype=torch.int32, device=dev)
+    plist = torch.zeros(F, H * W, dtype=torch.int32, device=dev)    # uint32 entries: pixel | code << 24, 0 = none
     cnt = torch.zeros(F, dtype=torch.int32, device=dev)
+    kctr = torch.zeros(2, dtype=torch.int32, device=dev)             # device-side iteration index (csrc/poisson.cu)
     L = lib.load()
     sp = lib.stream_ptr
     lib.check(L.fgt_poisson_setup(trg.data_ptr(), gx.data_ptr(), gy.data_ptr(), hole.data_ptr(), _ptr(gmask), _ptr(edge),
@@ -73,19 +78,29 @@ def poisson_blend_batch(trg, gx, gy, hole, gmask=None, edge=None, device=None, r
     lib.COUNTERS["launches"] += 2
     iter_lim = 2 * H * W
     max_cnt = int(cnt.max())                           # pixels owning equations, largest frame (one host sync)
+    iter_args = (plist.data_ptr(), max_cnt, F, H, W, u.data_ptr(), v.data_ptr(), w.data_ptr(), x.data_ptr(),
+                 bb.data_ptr(), aa.data_ptr(), ww.data_ptr(), state.data_ptr(), kctr.data_ptr(), CHUNK, atol, btol,
+                 conlim, iter_lim)
+    exec_ = ctypes.c_void_p()
+    if use_graph:
+        lib.check(L.fgt_poisson_graph_create(*iter_args, ctypes.byref(exec_)), "fgt_poisson_graph_create")
     k = 0
-    while True:
-        n = min(CHUNK, max_iters + 1 - k)
-        if n <= 0:
-            raise RuntimeError(f"poisson: LSQR did not stop within {max_iters} iterations")
-        lib.check(L.fgt_poisson_iters(code.data_ptr(), plist.data_ptr(), cnt.data_ptr(), max_cnt, F, H, W, u.data_ptr(), v.data_ptr(), w.data_ptr(), x.data_ptr(),
-                                      bb.data_ptr(), aa.data_ptr(), ww.data_ptr(), state.data_ptr(), k, n,
-                                      atol, btol, conlim, iter_lim, sp()), "fgt_poisson_iters")
-        lib.COUNTERS["launches"] += 2 * n
-        k += n
-        last = state[(k - 1) & 1]                     # written by iteration k-1
-        if bool((last[:, 12] != 0).all()):             # one host sync per CHUNK iterations
-            break
+    try:
+        while True:
+            if k > max_iters:
+                raise RuntimeError(f"poisson: LSQR did not stop within {max_iters} iterations")
+            if use_graph:
+                lib.check(L.fgt_poisson_graph_launch(exec_, sp()), "fgt_poisson_graph_launch")
+            else:
+                lib.check(L.fgt_poisson_iters(*iter_args, sp()), "fgt_poisson_iters")
+            lib.COUNTERS["launches"] += 2 * CHUNK
+            k += CHUNK
+            last = state[(k - 1) & 1]                     # written by iteration k-1
+            if bool((last[:, 12] != 0).all()):             # one host sync per CHUNK iterations
+                break
+    finally:
+        if exec_:
+            L.fgt_poisson_graph_destroy(exec_)
     out = torch.empty_like(trg)
     unf = torch.empty(F, H, W, dtype=torch.uint8, device=dev)
     lib.check(L.fgt_poisson_finish(trg.data_ptr(), hole.data_ptr(), x.data_ptr(), F, H, W, out.data_ptr(),

@@ -205,14 +205,18 @@ int fgt_regionfill_finish(const double* img, const unsigned char* mask, long lon
  * All vectors fp64, channels-last; caller-owned, ZERO-INITIALISED device memory unless noted:
  *   trg [F,H,W,3], gx [F,H,W-1,3], gy [F,H-1,W,3] (forward differences); hole / gmask / edge uint8 [F,H,W]
  *   (gmask, edge may be NULL = all zero); code uint8 [F,H,W]; u [F,4,H*W,3]; v, w, x [F,H*W,3];
- *   bb, aa, ww: (max_iters+2) * 3F per-iteration sums (slot k*3F + s); state [2, 3F, 16] (ping-pong by iteration
+ *   bb, aa, ww: (max_iters + chunk + 2) * 3F per-iteration sums (slot k*3F + s); state [2, 3F, 16] (ping-pong by iteration
  *   parity; per system s = 3*frame + channel: [12] = stopped, [13] = scipy's istop, [14] = itn).
  *   fgt_poisson_setup   : equation codes, u = b, bb[0] = |b|^2 (constructEquation :176-266); appends the pixels
- *                         that own equations to list [F,H*W] int32 and counts them in cnt [F] (zero-initialised) —
- *                         the host reads max(cnt) once and passes it as max_cnt, so the iteration kernels launch
- *                         threads for those pixels only
- *   fgt_poisson_iters   : k = k0 .. k0+iters-1; k = 0 finishes the set-up (v = A^T u / alfa, w = v), k >= 1 is
- *                         LSQR iteration k; two kernels per k; systems that have stopped stay frozen
+ *                         that own equations to list [F,H*W] uint32 (pixel index | code << 24; zero-initialised, H*W <
+ *                         2^24) and counts them in cnt [F] (zero-initialised) — the host reads max(cnt) once and
+ *                         passes it as max_cnt, so the iteration kernels launch threads for those pixels only
+ *   fgt_poisson_iters   : the next `iters` values of the iteration index k, which lives on the device (kctr: 2 int32,
+ *                         zero-initialised): k = 0 finishes the set-up (v = A^T u / alfa, w = v), k >= 1 is LSQR
+ *                         iteration k; two kernels per k; systems that have stopped stay frozen
+ *   fgt_poisson_graph_* : the same `iters` kernel pairs captured once into an executable CUDA graph (a host-side driver
+ *                         object, the only thing this library ever creates; destroy it with _graph_destroy) and
+ *                         replayed with _graph_launch — every replay continues at the device-side k
  *   fgt_poisson_unfilled: the two raster sweeps of the connectivity check (:139-172) -> clr [2,F,H,W]
  *   fgt_poisson_finish  : out = hole ? float64(float32(x)) : trg (:29,40-44); unf = hole & !clr[0] & !clr[1]
  *                         (unf / clr may be NULL)
@@ -221,10 +225,15 @@ int fgt_regionfill_finish(const double* img, const unsigned char* mask, long lon
  *                         = {t1, t2, vscale, alfa*uscale, skip_all, skip_u}. For tests of the stopping logic. */
 int fgt_poisson_setup(const double* trg, const double* gx, const double* gy, const unsigned char* hole,
                       const unsigned char* gmask, const unsigned char* edge, int F, int H, int W, unsigned char* code,
-                      double* u, double* bb, int* list, int* cnt, fgt_stream_t stream);
-int fgt_poisson_iters(const unsigned char* code, const int* list, const int* cnt, int max_cnt, int F, int H, int W,
-                      double* u, double* v, double* w, double* x, double* bb, double* aa, double* ww, double* state,
-                      int k0, int iters, double atol, double btol, double conlim, int iter_lim, fgt_stream_t stream);
+                      double* u, double* bb, unsigned* list, int* cnt, fgt_stream_t stream);
+int fgt_poisson_iters(const unsigned* list, int max_cnt, int F, int H, int W, double* u, double* v, double* w, double* x,
+                      double* bb, double* aa, double* ww, double* state, int* kctr, int iters, double atol, double btol,
+                      double conlim, int iter_lim, fgt_stream_t stream);
+int fgt_poisson_graph_create(const unsigned* list, int max_cnt, int F, int H, int W, double* u, double* v, double* w,
+                             double* x, double* bb, double* aa, double* ww, double* state, int* kctr, int iters,
+                             double atol, double btol, double conlim, int iter_lim, void** exec_out);
+int fgt_poisson_graph_launch(void* exec, fgt_stream_t stream);
+int fgt_poisson_graph_destroy(void* exec);
 int fgt_poisson_unfilled(const unsigned char* hole, const unsigned char* gmask, int F, int H, int W, unsigned char* clr,
                          fgt_stream_t stream);
 int fgt_poisson_finish(const double* trg, const unsigned char* hole, const double* x, int F, int H, int W, double* out,

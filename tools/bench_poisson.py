@@ -36,21 +36,27 @@ t64 = lambda a: torch.as_tensor(a).to(dev, torch.float64).contiguous()
 a_trg, a_gx, a_gy = t64(trg), t64(gx), t64(gy)
 a_hole, a_gm = torch.as_tensor(hole).to(dev), torch.as_tensor(gm).to(dev)
 torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 before = lib.COUNTERS["launches"]
-e0.record()
 P.poisson_blend_batch(a_trg, a_gx, a_gy, a_hole, a_gm)
-e1.record()
-torch.cuda.synchronize()
 launches = lib.COUNTERS["launches"] - before
-res["ms_per_clip_device_resident"] = e0.elapsed_time(e1)
+for mode, key in ((True, "ms_per_clip_device_resident"), (False, "ms_per_clip_device_resident_stream_launches")):
+    best = 1e9
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        P.poisson_blend_batch(a_trg, a_gx, a_gy, a_hole, a_gm, use_graph=mode)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    res[key] = best
 res["kernel_launches"] = launches
 n_eq_pix = int((np.stack([PO.equation_codes(hole[f], gm[f], np.zeros_like(hole[f])) for f in range(F)]) & 15).astype(bool).sum())
 # algorithmic bytes of one iteration per pixel that owns equations (fp64, 3 channels):
 #   psn_v: read u 4x3 + neighbours' u 4x3 + v 3, write v 3            = 30 doubles
 #   psn_ux: read v 3 + neighbours' v 4x3 + w 3 + x 3 + u 4x3, write x, w 3+3, u 4x3 = 51 doubles
 res["algorithmic_bytes_per_iteration"] = n_eq_pix * 81 * 8
-iters = int(itn.max()) + 1
+iters = -(-(int(itn.max()) + 1) // P.CHUNK) * P.CHUNK      # whole chunks are replayed
 res["achieved_GBps_over_all_iterations"] = res["algorithmic_bytes_per_iteration"] * iters / (res["ms_per_clip_device_resident"] * 1e-3) / 1e9
 res["us_per_iteration"] = res["ms_per_clip_device_resident"] * 1e3 / iters
 
