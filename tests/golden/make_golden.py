@@ -219,6 +219,10 @@ def poisson_case(name, F, H, W, seed, with_edge):
 
 
 if __name__ == "__main__":
+    if "--extra-only" in sys.argv:     # the driver's default working size (imgH=256, :829) on a 240x432 checkpoint; RAFT at 720p
+        fgt_case("fgt_driver_256x432_t6", 256, 432, 6, "scaled", (240, 432), seed=6, sample=16384)
+        raft_case("raft_720p_i20", 720, 1280, 20, seed=7, sample=8192)
+        sys.exit(0)
     if "--flo-only" in sys.argv:       # 3x5 flow written by the reference's writer (tests/test_io.py)
         sys.path.insert(0, os.path.join(REF, "RAFT"))
         from utils import frame_utils as FU

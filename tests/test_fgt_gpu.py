@@ -116,3 +116,15 @@ def test_clip_streamer_matches_direct_calls():
         for i, (a, b) in enumerate(zip(got, direct)):
             assert torch.equal(a, b), f"clip {i} (graph={graph})"
     model.net.enable_cuda_graph(False)
+
+
+def test_fgt_driver_default_size_256x432():
+    """The driver's default working size (--imgH 256 --imgW 432, tool/video_inpainting.py:829-830) on a checkpoint
+    configured for 240x432: runtime geometry 22x36 tokens (temporal zones 11x18, spatial grid padded to 24x40), first
+    window of a 10-frame clip (t=6). Sampled reference output + norm."""
+    g = load_golden("fgt_driver_256x432_t6")
+    out, _, _, _ = _run(g["meta"])
+    assert tuple(out.shape) == (6, 3, 256, 432)
+    assert torch.isfinite(out).all()
+    assert_close(out.reshape(-1).cpu()[torch.from_numpy(g["idx"])], g["val"], REL_TOL, "fgt_driver_256x432 samples")
+    assert abs(out.double().norm().item() - float(g["l2"])) / float(g["l2"]) < REL_TOL

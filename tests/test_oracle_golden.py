@@ -50,3 +50,12 @@ def test_oracle_modules():
     for name, val in (("swmhsa", sw), ("tmhsa", tm), ("ffn", ff)):
         assert_close(val.reshape(-1)[idx], g[name], ORACLE_TOL, name)
         assert abs(val.double().norm().item() - float(g[name + "_l2"])) / float(g[name + "_l2"]) < 1e-5
+
+
+def test_oracle_driver_default_size_256x432():
+    """Runtime geometry of the driver's default 256x432 working size on a 240x432 checkpoint."""
+    g = load_golden("fgt_driver_256x432_t6")
+    out = _run_oracle(g["meta"])
+    assert tuple(out.shape) == (6, 3, 256, 432)
+    assert_close(out.reshape(-1)[torch.from_numpy(g["idx"])], g["val"], ORACLE_TOL, "fgt_driver_256x432 samples")
+    assert abs(out.double().norm().item() - float(g["l2"])) / float(g["l2"]) < 1e-5

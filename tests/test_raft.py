@@ -113,6 +113,21 @@ def test_raft_gpu_full_480x864():
 
 
 @pytest.mark.gpu
+def test_raft_gpu_720p():
+    """BASELINE config 5 geometry: at imgH >= 350 the driver feeds RAFT the working resolution itself (720x1280 ->
+    90x160 features, 14 400^2 all-pairs correlation = 829 MB at level 0)."""
+    g = load_golden("raft_720p_i20")
+    m = g["meta"]
+    model, _ = _gpu_model(m["seed"])
+    im1, im2 = synth.raft_inputs(seed=m["seed"] + 1, H=m["H"], W=m["W"])
+    with torch.no_grad():
+        lo, up = model(im1.cuda(), im2.cuda(), iters=m["iters"], test_mode=True)
+    assert tuple(up.shape) == (1, 2, 720, 1280)
+    assert_close(lo, g["lo"], REL_TOL, "raft_720p low")
+    assert_close(up.reshape(-1).cpu()[torch.from_numpy(g["up_idx"])], g["up_val"], REL_TOL, "raft_720p up samples")
+
+
+@pytest.mark.gpu
 def test_raft_helper_kernels():
     from fgt_b200 import lib
     dev = torch.device("cuda:0")
