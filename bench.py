@@ -291,12 +291,32 @@ def main():
                 model.net.enable_frame_sharding(None)
         return out
 
+    def timed_driver_schedule():
+        """the driver's own window schedule for a 10-frame clip (tool/video_inpainting.py:709-717 with
+        step 10, stride 5): f=0 -> 6 frames, f=5 -> all 10; frames/s = 10 emitted frames / (t6 + t10). Device-resident
+        inputs, same event timing as `value`."""
+        sched = parallel.window_schedule(T)
+        ms = []
+        for _, nb, ref in sched:
+            ids = nb + ref
+            part = [t[:, ids].contiguous() for t in devin]
+            m, _ = timed(lambda: model(*part))
+            ms.append(m)
+        return {"windows_t": [len(nb) + len(ref) for _, nb, ref in sched], "ms_per_window": ms,
+                "value": T * world / (sum(ms) * 1e-3), "unit": "frames/s",
+                "note": "10 output frames per clip / time of the clip's two windows (6 + 10 input frames)"}
+
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms_dev, launches = timed(step_device)
     ms_e2e_serial, _ = timed(step_e2e)
     ms_e2e, streamer = timed_streamed()
     clocks = sampler.stop()
+    driver_sched = None
+    try:
+        driver_sched = timed_driver_schedule()
+    except Exception as exc:  # noqa: BLE001 - an extra line, never fatal for the main measurement
+        print(f"[bench] driver-schedule measurement failed: {exc}", file=sys.stderr)
 
     # per-kernel breakdown: CUDA events around every launch of 3 more forwards (not part of `value`)
     peaks = load_peaks()
@@ -383,6 +403,7 @@ def main():
                                "note": "one T=10 window split by frames over the ranks; per temporal layer the "
                                        "LayerNorm kernel stores its rows into all peers' K/V-input buffers over "
                                        "NVLink (fused exchange, CUDA-graph replay) vs. NCCL all-gather (eager)"}),
+            "driver_schedule": driver_sched,
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels,
             "cpu_baseline": cpu, "impl": "fgt_b200",
         }), file=RESULT_OUT, flush=True)
