@@ -165,6 +165,7 @@ class GpuBackend:
             raise RuntimeError("fgt_b200.pipeline.GpuBackend needs a CUDA (sm_100a) device; there is no CPU fallback")
         self.dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.raft, self.lafc, self.fgt = raft, lafc, fgt
+        self.fgt_model = fgt          # the callable the FGT stage evaluates per window (ShardedBackend swaps it)
         self.raft_batch = raft_batch
 
     def raft_pairs(self, img1, img2, iters):
@@ -205,7 +206,126 @@ class GpuBackend:
 
     def fgt_stage(self, frame_blends, mask, flow_f, step, num_ref, neighbor_stride):
         from .clip import inpaint_clip
-        return inpaint_clip(self.fgt, frame_blends, mask, flow_f, step, num_ref, neighbor_stride, device=self.dev)
+        return inpaint_clip(self.fgt_model, frame_blends, mask, flow_f, step, num_ref, neighbor_stride, device=self.dev)
+
+
+class ShardedBackend:
+    """Multi-GPU execution of the pipeline: wraps any backend and shards the independent work items
+    of every stage over the ranks of a torch.distributed group — RAFT pairs, diffusion solves, LAFC triplets, Poisson
+    frames, FGT windows (balanced by frames per window) — with one all-gather per stage, so that every rank holds the
+    complete stage output (131 MB of flows at N=80, 240x432) before the next stage starts. The propagation is
+    sequential over frames and runs replicated. One process per GPU (torchrun); NCCL moves device tensors over
+    NVLink, gloo (CPU tests) host tensors. Results are bit-identical to the unsharded backend: every item is
+    computed by exactly the same call, only by a different rank."""
+
+    def __init__(self, inner, group=None):
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("ShardedBackend needs an initialised torch.distributed process group")
+        self.inner, self.group, self.dist = inner, group, dist
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        nccl = dist.get_backend(group) == "nccl"
+        self.comm_dev = torch.device("cuda", torch.cuda.current_device()) if nccl else torch.device("cpu")
+
+    def _mine(self, n, costs=None):
+        from .parallel import shard_items
+        return shard_items(n, self.rank, self.world, costs)
+
+    def _gather(self, local, n, costs=None):
+        """local: array [k, ...] of this rank's items (k may be 0 -> pass the trailing shape via a [0, ...] array);
+        returns [n, ...] in item order on every rank."""
+        from .parallel import shard_items
+        owners = [shard_items(n, r, self.world, costs) for r in range(self.world)]
+        kmax = max(len(o) for o in owners)
+        local = np.ascontiguousarray(local)
+        pad = np.zeros((kmax,) + local.shape[1:], dtype=local.dtype)
+        pad[:local.shape[0]] = local
+        t = torch.from_numpy(pad.view(np.uint8).reshape(kmax, -1)).to(self.comm_dev)
+        parts = [torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(parts, t.contiguous(), group=self.group)           # raw bytes: exact on every backend
+        out = np.zeros((n,) + local.shape[1:], dtype=local.dtype)
+        for r, ids in enumerate(owners):
+            if ids:
+                rows = parts[r].cpu().numpy().view(local.dtype).reshape((kmax,) + local.shape[1:])
+                out[ids] = rows[:len(ids)]
+        return out
+
+    def raft_pairs(self, img1, img2, iters):
+        n = img1.shape[0]
+        mine = self._mine(n)
+        h, w = img1.shape[2], img1.shape[3]
+        local = self.inner.raft_pairs(img1[mine], img2[mine], iters) if mine else np.zeros((0, 2, h, w), np.float32)
+        return self._gather(np.asarray(local, dtype=np.float32), n)
+
+    def diffusion(self, flows, masks):
+        n = flows.shape[0]
+        mine = self._mine(n)
+        local = np.stack(self.inner.diffusion(flows[mine], masks[mine]), 0) if mine else np.zeros((0,) + flows.shape[1:], np.float64)
+        out = self._gather(np.asarray(local, dtype=np.float64), n)
+        return [out[i] for i in range(n)]
+
+    def lafc_complete(self, flows, masks, diffused, triplets, pivot):
+        n = len(triplets)
+        mine = self._mine(n)
+        H, W = flows.shape[2], flows.shape[3]
+        local = self.inner.lafc_complete(flows, masks, diffused, [triplets[i] for i in mine], pivot) if mine else np.zeros((0, 2, H, W), np.float32)
+        return self._gather(np.asarray(local, dtype=np.float32), n)
+
+    def propagate(self, *a):
+        return self.inner.propagate(*a)                       # sequential over frames: replicas only
+
+    def poisson_frames(self, trg, gx, gy, hole, gmask):
+        n = len(trg)
+        mine = self._mine(n)
+        pick = lambda xs: [xs[i] for i in mine]
+        res = self.inner.poisson_frames(pick(trg), pick(gx), pick(gy), pick(hole), pick(gmask)) if mine else []
+        shp = tuple(np.asarray(trg[0]).shape)
+        blend = np.stack([r[0] for r in res], 0) if res else np.zeros((0,) + shp, np.float64)
+        unf = np.stack([r[1] for r in res], 0).astype(np.uint8) if res else np.zeros((0,) + shp[:2], np.uint8)
+        blend, unf = self._gather(np.asarray(blend, dtype=np.float64), n), self._gather(unf, n)
+        return [(blend[i], unf[i].astype(bool)) for i in range(n)]
+
+    def fgt_stage(self, frame_blends, mask, flow_f, step, num_ref, neighbor_stride):
+        """Windows shard over the ranks (cost = frames per window). Pass 1: the stage runs with a model proxy that
+        evaluates only this rank's windows (the others return zeros; the composite of this pass is discarded) and
+        keeps their outputs; all-gather; pass 2: the stage runs again with a proxy that replays every window's output,
+        so the compositing — including the order-dependent 0.5/0.5 averaging — is exactly the unsharded one."""
+        from .parallel import window_schedule
+        sched = window_schedule(len(frame_blends), neighbor_stride, step, num_ref)
+        costs = [len(nb) + len(ref) for _, nb, ref in sched]
+        mine = set(self._mine(len(sched), costs))
+        real, kept, calls = self.inner.fgt_model, {}, [0]
+
+        def first_pass(frames, flows, masks):
+            wi = calls[0]
+            calls[0] += 1
+            if wi in mine:
+                kept[wi] = real(frames, flows, masks)
+                return kept[wi]
+            return torch.zeros(frames.shape[1], 3, frames.shape[3], frames.shape[4], dtype=torch.float32, device=frames.device)
+
+        try:
+            self.inner.fgt_model = first_pass
+            self.inner.fgt_stage(frame_blends, mask, flow_f, step, num_ref, neighbor_stride)
+            tmax = max(costs)
+            some = next(iter(kept.values())) if kept else None
+            H, W = np.asarray(frame_blends[0]).shape[:2]
+            local = np.zeros((len(kept), tmax, 3, H, W), np.float32)
+            for j, wi in enumerate(sorted(kept)):
+                local[j, :costs[wi]] = kept[wi].detach().float().cpu().numpy()
+            allw = self._gather(local, len(sched), costs)
+            dev = some.device if some is not None else None
+            calls[0] = 0
+
+            def second_pass(frames, flows, masks):
+                wi = calls[0]
+                calls[0] += 1
+                return torch.from_numpy(allw[wi, :costs[wi]]).to(frames.device if dev is None else dev)
+
+            self.inner.fgt_model = second_pass
+            return self.inner.fgt_stage(frame_blends, mask, flow_f, step, num_ref, neighbor_stride)
+        finally:
+            self.inner.fgt_model = real
 
 
 # ------------------------------------------------------------------------------------------------ driver

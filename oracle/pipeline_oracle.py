@@ -16,6 +16,7 @@ class OracleBackend:
     def __init__(self, raft_sd, lafc_sd, fgt_sd):
         """State dicts without the wrappers' prefixes ('module.' for RAFT, 'net.' for LAFC / FGT)."""
         self.raft_sd, self.lafc_sd, self.fgt_sd = raft_sd, lafc_sd, fgt_sd
+        self.fgt_model = lambda a, b, c: fgt_oracle.fgt_forward(self.fgt_sd, a, b, c)   # swapped by ShardedBackend
 
     def raft_pairs(self, img1, img2, iters):
         with torch.no_grad():
@@ -46,5 +47,4 @@ class OracleBackend:
         return [poisson_oracle.poisson_blend(t, a, b, h, g) for t, a, b, h, g in zip(trg, gx, gy, hole, gmask)]
 
     def fgt_stage(self, frame_blends, mask, flow_f, step, num_ref, neighbor_stride):
-        model = lambda a, b, c: fgt_oracle.fgt_forward(self.fgt_sd, a, b, c)
-        return clip_oracle.fgt_stage(model, frame_blends, mask, flow_f, step, num_ref, neighbor_stride)
+        return clip_oracle.fgt_stage(self.fgt_model, frame_blends, mask, flow_f, step, num_ref, neighbor_stride)

@@ -140,3 +140,51 @@ def test_gpu_command_line_end_to_end(tmp_path):
     assert len(back) == len(frames) and all(np.array_equal(a, b) for a, b in zip(back, comp))
     diff = np.abs(np.stack(comp).astype(np.int16) - g["comp"].astype(np.int16))
     assert diff.max() <= 8 and diff.mean() < 0.05
+
+
+# ------------------------------------------------------------------------------------------------ multi-rank (gloo)
+def _sharded_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from oracle.pipeline_oracle import OracleBackend
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(4)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g, st, frames, masks, args, cfg, sds = _setup()
+        inner = OracleBackend(sds["raft"], O.strip_net(sds["lafc"]), O.strip_net(sds["fgt"]))
+        be = PL.ShardedBackend(inner)
+        calls = {"raft": 0, "fgt": 0}
+        raft0, fgt0 = inner.raft_pairs, inner.fgt_model
+        inner.raft_pairs = lambda a, b, it: (calls.__setitem__("raft", calls["raft"] + a.shape[0]), raft0(a, b, it))[1]
+        inner.fgt_model = lambda a, b, c: (calls.__setitem__("fgt", calls["fgt"] + 1), fgt0(a, b, c))[1]
+        comp, stages = PL.video_inpainting(frames, masks, be, args, return_stages=True)
+        assert inner.fgt_model is not None
+        q.put((rank, np.stack(comp), stages["done_f"], np.asarray(stages["mask_gradient"], bool), dict(calls)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_pipeline_gloo_world2_matches_reference_driver():
+    """SURVEY 8e on the CPU: two ranks, every stage's items sharded + all-gathered; both ranks end with the frames of
+    the unmodified reference driver, and each rank evaluated only its share of the RAFT pairs and FGT windows."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    g, st = load_golden("pipeline_clip"), load_golden("pipeline_stages")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=600) for _ in procs], key=lambda r: r[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    (_, comp0, done0, mg0, calls0), (_, comp1, done1, mg1, calls1) = res
+    assert np.array_equal(comp0, comp1) and np.array_equal(done0, done1) and np.array_equal(mg0, mg1)
+    diff = np.abs(comp0.astype(np.int16) - g["comp"].astype(np.int16))
+    assert diff.max() <= 1 and (diff != 0).mean() < 1e-3
+    assert np.abs(done0 - np.moveaxis(g["flow_f"], 0, -1)).max() < 1e-3
+    # 6 forward + 6 backward pairs split 3+3 per direction; 2 windows split 1+1
+    assert calls0 == {"raft": 6, "fgt": 1} and calls1 == {"raft": 6, "fgt": 1}

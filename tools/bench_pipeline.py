@@ -39,7 +39,7 @@ class Timed:
         return call
 
 
-def models(H, W, seeds=(31, 32, 33)):
+def models(H, W, seeds=(31, 32, 33), dev=dev):
     cfg = dict(synth.CFG_A)
     cfg["input_resolution"] = (H, W)
     sds = dict(fgt=synth.make_state_dict(synth.fgt_param_shapes(cfg), seed=seeds[0]),
@@ -71,19 +71,24 @@ def run(N, H, W, reps):
     return best, frames, masks, args, sds, out
 
 
-res = {}
-best, frames, masks, args, sds, out = run(7, 64, 96, 3)
-res["clip_7x64x96"] = best
-if "--no-cpu" not in sys.argv:
-    from oracle import fgt_oracle as O
-    from oracle.pipeline_oracle import OracleBackend
-    ob = Timed(OracleBackend(sds["raft"], O.strip_net(sds["lafc"]), O.strip_net(sds["fgt"])), False)
-    t0 = time.perf_counter()
-    ref = PL.video_inpainting(frames, masks, ob, args)
-    tot = time.perf_counter() - t0
-    d = np.abs(np.stack(out).astype(np.int16) - np.stack(ref).astype(np.int16))
-    res["clip_7x64x96"]["cpu_oracle"] = dict(seconds=tot, frames_per_s=7 / tot, stage_seconds={k: round(v, 3) for k, v in ob.t.items()},
-                                             threads=torch.get_num_threads(), mean_abs_diff_levels=float(d.mean()),
-                                             frac_over_2_levels=float((d > 2).mean()))
-res["clip_10x240x432"] = run(10, 240, 432, 2)[0]
-print(json.dumps(res))
+def main():
+    res = {}
+    best, frames, masks, args, sds, out = run(7, 64, 96, 3)
+    res["clip_7x64x96"] = best
+    if "--no-cpu" not in sys.argv:
+        from oracle import fgt_oracle as O
+        from oracle.pipeline_oracle import OracleBackend
+        ob = Timed(OracleBackend(sds["raft"], O.strip_net(sds["lafc"]), O.strip_net(sds["fgt"])), False)
+        t0 = time.perf_counter()
+        ref = PL.video_inpainting(frames, masks, ob, args)
+        tot = time.perf_counter() - t0
+        d = np.abs(np.stack(out).astype(np.int16) - np.stack(ref).astype(np.int16))
+        res["clip_7x64x96"]["cpu_oracle"] = dict(seconds=tot, frames_per_s=7 / tot, stage_seconds={k: round(v, 3) for k, v in ob.t.items()},
+                                                 threads=torch.get_num_threads(), mean_abs_diff_levels=float(d.mean()),
+                                                 frac_over_2_levels=float((d > 2).mean()))
+    res["clip_10x240x432"] = run(10, 240, 432, 2)[0]
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
