@@ -37,9 +37,19 @@ from fgt_b200 import synth  # noqa: E402
 
 H, W, N = 64, 96, 7
 CAPTURE = {}
+# second case (--second): 12 frames -> three windows (f = 0, 5, 10), frames visited up to three times
+# (0.25 / 0.25 / 0.5 averaging), a reference frame outside the neighbourhood, no frame dilation (uint8 mask branch,
+# :556-561), other seeds. Only the final frames and the propagation mask are stored (pipeline12.npz).
+SECOND = dict(N=12, clip_seed=9, fgt_seed=41, lafc_seed=42, raft_seed=43, flow_mask_dilates=2, frame_dilates=0)
 
 
-def main():
+def main(second=False):
+    global N
+    cs, fs, ls, rs, fmd, fd = 5, 31, 32, 33, 3, 1
+    if second:
+        N = SECOND["N"]
+        cs, fs, ls, rs = SECOND["clip_seed"], SECOND["fgt_seed"], SECOND["lafc_seed"], SECOND["raft_seed"]
+        fmd, fd = SECOND["flow_mask_dilates"], SECOND["frame_dilates"]
     for m in ("cvbase", "imageio", "skimage", "skimage.feature"):
         sys.modules.setdefault(m, types.ModuleType(m))
     sys.modules["skimage.feature"].canny = None
@@ -49,7 +59,7 @@ def main():
 
     tmp = tempfile.mkdtemp(prefix="fgt_pipeline_")
     try:
-        frames, masks = synth.pipeline_clip(seed=5, N=N, H=H, W=W)
+        frames, masks = synth.pipeline_clip(seed=cs, N=N, H=H, W=W)
         for d in ("frames", "masks", "fgt_ckpt", "lafc_ckpt", "out"):
             os.makedirs(os.path.join(tmp, d))
         for i, (fr, m) in enumerate(zip(frames, masks)):
@@ -57,27 +67,27 @@ def main():
             Image.fromarray(m).save(os.path.join(tmp, "masks", "%05d.png" % i))
         cfg = dict(synth.CFG_A)
         cfg["input_resolution"] = (H, W)
-        fgt_sd = synth.make_state_dict(synth.fgt_param_shapes(cfg), seed=31)
+        fgt_sd = synth.make_state_dict(synth.fgt_param_shapes(cfg), seed=fs)
         torch.save({"model_state_dict": fgt_sd}, os.path.join(tmp, "fgt_ckpt", "fgt.tar"))
         ycfg = {k: (list(v) if isinstance(v, tuple) else v) for k, v in cfg.items()}
         ycfg["model"] = "model"
         with open(os.path.join(tmp, "fgt_ckpt", "config.yaml"), "w") as fh:
             yaml.safe_dump(ycfg, fh)
-        lafc_sd = synth.make_state_dict(synth.lafc_param_shapes(synth.CFG_LAFC), seed=32)
+        lafc_sd = synth.make_state_dict(synth.lafc_param_shapes(synth.CFG_LAFC), seed=ls)
         torch.save({"model_state_dict": lafc_sd}, os.path.join(tmp, "lafc_ckpt", "lafc.tar"))
         with open(os.path.join(tmp, "lafc_ckpt", "config.yaml"), "w") as fh:
             yaml.safe_dump(dict(synth.CFG_LAFC), fh)
-        raft_sd = synth.raft_state_dict(seed=33)
+        raft_sd = synth.raft_state_dict(seed=rs)
         torch.save({"module." + k: v for k, v in raft_sd.items()}, os.path.join(tmp, "raft.pth"))
         opt = os.path.join(tmp, "opt.yaml")
         with open(opt, "w") as fh:
-            yaml.safe_dump(dict(mode="object_removal", consistencyThres=5, alpha=0.1, flow_mask_dilates=3, frame_dilates=1), fh)
+            yaml.safe_dump(dict(mode="object_removal", consistencyThres=5, alpha=0.1, flow_mask_dilates=fmd, frame_dilates=fd), fh)
         args = argparse.Namespace(
             opt=opt, mode="object_removal", path=os.path.join(tmp, "frames"), path_mask=os.path.join(tmp, "masks"),
             outroot=os.path.join(tmp, "out"), consistencyThres=5.0, alpha=0.1, Nonlocal=False,
             raft_model=os.path.join(tmp, "raft.pth"), small=False, mixed_precision=False,
             alternate_corr=False, lafc_ckpts=os.path.join(tmp, "lafc_ckpt"), fgt_ckpts=os.path.join(tmp, "fgt_ckpt"),
-            H_scale=2, W_scale=2, imgH=H, imgW=W, flow_mask_dilates=3, frame_dilates=1, gpu=0, step=10, num_ref=-1,
+            H_scale=2, W_scale=2, imgH=H, imgW=W, flow_mask_dilates=fmd, frame_dilates=fd, gpu=0, step=10, num_ref=-1,
             neighbor_stride=5, vis_flows=False, vis_completed_flows=False, vis_prop=False, vis_frame=False)
 
         # hooks: record, then call the unmodified function
@@ -121,12 +131,17 @@ def main():
 
     import cv2
     import scipy
-    meta = dict(H=H, W=W, N=N, fgt_seed=31, lafc_seed=32, raft_seed=33, clip_seed=5, flow_mask_dilates=3, frame_dilates=1, torch=torch.__version__, numpy=np.__version__,
+    meta = dict(H=H, W=W, N=N, fgt_seed=fs, lafc_seed=ls, raft_seed=rs, clip_seed=cs, flow_mask_dilates=fmd, frame_dilates=fd, torch=torch.__version__, numpy=np.__version__,
                 scipy=scipy.__version__, cv2=cv2.__version__)
     frame_blends, mask, flow_f = t_calls            # the three near="t" conversions of the FGT stage, in order
     comp = np.stack(CAPTURE["comp_frames"])
     assert frame_blends.shape == (N, H, W, 3) and mask.shape == (N, H, W, 1) and flow_f.shape == (N, H, W, 2)
     assert comp.shape == (N, H, W, 3) and comp.dtype == np.uint8
+    if second:
+        np.savez_compressed(os.path.join(HERE, "pipeline12.npz"), meta=np.array(repr(meta)), comp=comp,
+                            mask_gradient=np.packbits(stages["mask_gradient"]), mask_final=np.packbits(mask.astype(bool)))
+        print("pipeline12 saved: comp mean", comp.mean(), "final holes", int(mask.sum()))
+        return
     # frame_blends as recorded are already RGB (the driver flips in place before np2tensor, :688-689)
     np.savez_compressed(os.path.join(HERE, "pipeline_clip.npz"), meta=np.array(repr(meta)),
                         frames_rgb=frame_blends, mask=np.packbits(mask.astype(bool)), flow_f=flow_f[:-1].astype(np.float32),
@@ -147,4 +162,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(second="--second" in sys.argv)

@@ -188,3 +188,28 @@ def test_sharded_pipeline_gloo_world2_matches_reference_driver():
     assert np.abs(done0 - np.moveaxis(g["flow_f"], 0, -1)).max() < 1e-3
     # 6 forward + 6 backward pairs split 3+3 per direction; 2 windows split 1+1
     assert calls0 == {"raft": 6, "fgt": 1} and calls1 == {"raft": 6, "fgt": 1}
+
+
+def test_pipeline_glue_second_reference_run_12_frames():
+    """A second full run of the unmodified reference driver (tests/golden/pipeline12.npz): 12 frames -> three windows,
+    frames composed from up to three visits (0.25 / 0.25 / 0.5), a reference frame outside the neighbourhood, no frame
+    dilation (the uint8-mask branch of the driver), different seeds for all three networks."""
+    from oracle.pipeline_oracle import OracleBackend
+    g = load_golden("pipeline12")
+    m = g["meta"]
+    from fgt_b200.parallel import window_schedule
+    assert m["N"] == 12 and [len(n) + len(r) for _, n, r in window_schedule(12)] == [7, 11, 8]
+    frames, masks = synth.pipeline_clip(seed=m["clip_seed"], N=m["N"], H=m["H"], W=m["W"])
+    args = PL.make_args(imgH=m["H"], imgW=m["W"], flow_mask_dilates=m["flow_mask_dilates"], frame_dilates=m["frame_dilates"])
+    cfg = dict(synth.CFG_A)
+    cfg["input_resolution"] = (m["H"], m["W"])
+    be = OracleBackend(synth.raft_state_dict(seed=m["raft_seed"]),
+                       O.strip_net(synth.make_state_dict(synth.lafc_param_shapes(synth.CFG_LAFC), seed=m["lafc_seed"])),
+                       O.strip_net(synth.make_state_dict(synth.fgt_param_shapes(cfg), seed=m["fgt_seed"])))
+    comp, stages = PL.video_inpainting(frames, masks, be, args, return_stages=True)
+    n = m["N"] * m["H"] * m["W"]
+    bits = lambda k: np.unpackbits(g[k])[:n]
+    assert np.array_equal(np.asarray(stages["mask_gradient"], bool).reshape(-1), bits("mask_gradient").astype(bool))
+    assert np.array_equal(np.moveaxis(stages["mask"], -1, 0).reshape(-1), bits("mask_final").astype(bool))
+    diff = np.abs(np.stack(comp).astype(np.int16) - g["comp"].astype(np.int16))
+    assert diff.max() <= 1 and (diff != 0).mean() < 1e-3, (diff.max(), (diff != 0).mean())
