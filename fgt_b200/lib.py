@@ -110,6 +110,10 @@ def load():
     lib.fgt_comp_to_u8.argtypes = [_c_p, cll, _c_p, _c_p]
     for fn in (lib.fgt_plane_max, lib.fgt_window_gather, lib.fgt_window_compose, lib.fgt_comp_to_u8):
         fn.restype = ctypes.c_int
+    lib.fgt_flow_splat.argtypes = [_c_p, _c_p, ci, ci, ci, ci, ci, _c_p, _c_p, _c_p]
+    lib.fgt_flow_splat.restype = ctypes.c_int
+    lib.fgt_flow_splat_targets_host.argtypes = [cf, cf, ci, ci, ci, ci, ci, _c_p, _c_p, _c_p, _c_p]
+    lib.fgt_flow_splat_targets_host.restype = ctypes.c_int
     lib.fgt_tapsum.argtypes = [_c_p, ci, ci, ci, ci, ci, ci, ci, ci, cll, _c_p, ci, _c_p, cll, cll, cll, cll, _c_p]
     lib.fgt_tapsum.restype = ctypes.c_int
     lib.fgt_dwpool.argtypes = [_c_p, ci, _c_p, ci, ci, ci, ci, ci, ci, ci, _c_p, _c_p, _c_p, _c_p]

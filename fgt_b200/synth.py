@@ -436,3 +436,17 @@ def pipeline_clip(seed=5, N=7, H=64, W=96):
         m[H // 3 + i:H // 3 + H // 4 + i, W // 3 + 2 * i:W // 3 + W // 4 + 2 * i] = 255
         masks.append(m)
     return frames, masks
+
+
+# ----------------------------------------------------------------------------------------------
+# forward flow splatting (LAFC/models/utils/flow_warp.py)
+# ----------------------------------------------------------------------------------------------
+def flow_warp_inputs(seed=0, b=2, c=5, h=20, w=28):
+    """Features [b,c,h,w] and a flow [b,2,h,w] with sub-pixel, exactly integer, negative and out-of-image targets."""
+    g = torch.Generator().manual_seed(seed)
+    feat = torch.randn(b, c, h, w, generator=g)
+    flow = torch.randn(b, 2, h, w, generator=g) * 3.0
+    flow[:, :, : h // 4] = torch.round(flow[:, :, : h // 4])          # integer displacements
+    flow[:, :, :, -2:] += 40.0                                         # pushed out of the image
+    flow[0, :, h // 2, : w // 2] = 0.0                                 # identity
+    return feat, flow

@@ -263,6 +263,19 @@ int fgt_window_compose(const float* filled, const float* frames, const unsigned 
 int fgt_comp_to_u8(const float* comp, long long total, unsigned char* out, fgt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Forward flow splatting (LAFC/models/utils/flow_warp.py:4-94, flow_prop / warp / sample_one): feat [B,C,H,W] is
+ * scattered along flow [B,2,H,W] (channel 0: column shift, channel 1: row shift, as in the reference) to the four
+ * integer neighbours of each target with weights exp(-d^2); out [B,C,H,W] = accumulated features / accumulated weight
+ * where the latter is positive; wsum [B,H,W] is workspace (both are zeroed by the call). backward != 0 negates the
+ * integer shifts (mode='backward'). */
+int fgt_flow_splat(const float* feat, const float* flow, int B, int C, int H, int W, int backward, float* out,
+                   float* wsum, fgt_stream_t stream);
+/* HOST-ONLY test hook: targets (row ti, column tj), weights and in-image flags of the four neighbours source pixel
+ * (i, j) is scattered to — the __host__ __device__ function the kernel calls. x = row shift, y = column shift. */
+int fgt_flow_splat_targets_host(float x, float y, int i, int j, int H, int W, int backward, int* ti_host, int* tj_host,
+                                float* wt_host, int* ok_host);
+
+/* ------------------------------------------------------------------------------------------
  * Peer memory for the multi-GPU exchange (no reference counterpart: the reference's inference is
  * single-device). One process per GPU; buffers are cudaMalloc'ed here (IPC-capable,
  * zero-initialised), exported as 64-byte CUDA IPC handles that the host side exchanges over its

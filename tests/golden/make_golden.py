@@ -223,6 +223,19 @@ if __name__ == "__main__":
         fgt_case("fgt_driver_256x432_t6", 256, 432, 6, "scaled", (240, 432), seed=6, sample=16384)
         raft_case("raft_720p_i20", 720, 1280, 20, seed=7, sample=8192)
         sys.exit(0)
+    if "--flowwarp-only" in sys.argv:  # LAFC/models/utils/flow_warp.py (dead code in the reference)
+        FW = importlib.import_module("LAFC.models.utils.flow_warp")
+        from oracle import flow_warp_oracle as FO
+        feat, flow = synth.flow_warp_inputs(seed=11)
+        outs = {}
+        for mode in ("forward", "backward"):
+            ref = FW.flow_prop(feat, flow, mode)
+            err = (FO.flow_prop(feat, flow, mode) - ref).abs().max().item()
+            assert err < 1e-5, err
+            outs[mode] = ref.numpy().astype(np.float32)
+            print("flow_warp", mode, "oracle vs reference max abs", err)
+        np.savez_compressed(os.path.join(HERE, "flow_warp.npz"), meta=np.array(repr(dict(seed=11, **VERSIONS))), **outs)
+        sys.exit(0)
     if "--flo-only" in sys.argv:       # 3x5 flow written by the reference's writer (tests/test_io.py)
         sys.path.insert(0, os.path.join(REF, "RAFT"))
         from utils import frame_utils as FU
