@@ -6,7 +6,6 @@ gradient propagation (prop_oracle), Poisson blending (poisson_oracle), the FGT s
 Plugging it into the pipeline glue and comparing with tests/golden/pipeline_*.npz — recorded from a full run of the
 unmodified reference driver tool/video_inpainting.py::video_inpainting — verifies the glue without a GPU.
 """
-import numpy as np
 import torch
 
 from . import clip_oracle, fgt_oracle, lafc_oracle, poisson_oracle, prop_oracle, raft_oracle, regionfill_oracle

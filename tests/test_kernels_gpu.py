@@ -1,6 +1,5 @@
 """GPU parity of the individual sm_100a kernels, called through the C-ABI (fgt_b200.lib), against
 fp64 PyTorch restatements of the same op on the same seeded inputs."""
-import math
 
 import pytest
 import torch

@@ -3,7 +3,6 @@ batched CG vs oracle and goldens on the GPU. fp64 throughout; tolerance 1e-7 abs
 magnitude ~10 (the CG stops at a relative residual of 1e-12)."""
 import numpy as np
 import pytest
-import torch
 
 from fgt_b200 import synth
 from oracle import regionfill_oracle as RO

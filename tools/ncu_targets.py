@@ -1,6 +1,5 @@
 """Small launch sets for ncu captures: `python tools/ncu_targets.py gemm|flash|model` runs the named
 kernels a few times on representative FGT shapes (432x240, T=10)."""
-import math
 import os
 import sys
 
