@@ -128,3 +128,33 @@ def test_hidden_permutation_matches_fold():
                 if 0 <= y < 15 and 0 <= x < 21:
                     img[0, :, y, x] += hp[0, ty, tx, p]
     assert torch.allclose(img, ref, atol=1e-5)
+
+
+def test_c_abi_rejects_bad_arguments_without_touching_the_gpu():
+    """Error behaviour of the boundary: a negative FGT_ERR_* code plus a thread-local message, checked
+    before any CUDA call — so it can be exercised on a host without a device."""
+    L = lib.load()
+    L.fgt_last_error.restype = ctypes.c_char_p
+    one = ctypes.c_void_p(8)                       # a non-null dummy; never dereferenced when validation fails first
+    calls = [
+        (L.fgt_poisson_setup, (None,) * 6 + (1, 4, 4) + (None,) * 6, "poisson_setup"),
+        (L.fgt_poisson_setup, (one,) * 6 + (1, 1, 4) + (one,) * 6, "poisson_setup"),                    # H < 2
+        (L.fgt_poisson_setup, (one,) * 6 + (1, 4096, 4096) + (one,) * 6, "2^24"),                      # H*W too large
+        (L.fgt_poisson_iters, (None, 0, 1, 4, 4) + (None,) * 9 + (1, 1e-6, 1e-6, 1e8, 32, None), "poisson_iters"),
+        (L.fgt_poisson_graph_launch, (None, None), "null graph"),
+        (L.fgt_poisson_unfilled, (None, None, 1, 4, 4, None, None), "poisson_unfilled"),
+        (L.fgt_poisson_finish, (None, None, None, 1, 4, 4, None, None, None, None), "poisson_finish"),
+        (L.fgt_plane_max, (None, 1, 16, None, None), "plane_max"),
+        (L.fgt_window_gather, (None,) * 5 + (1, 4, 4) + (None,) * 4, "window_gather"),
+        (L.fgt_window_compose, (None,) * 5 + (1, 4, 4, None, None), "window_compose"),
+        (L.fgt_comp_to_u8, (None, 16, None, None), "comp_to_u8"),
+        (L.fgt_flow_splat, (None, None, 1, 1, 4, 4, 0, None, None, None), "flow_splat"),
+        (L.fgt_regionfill_init, (None, None, 1, 4, 4, None, None, None, None, None), "regionfill_init"),
+    ]
+    for fn, args, needle in calls:
+        rc = fn(*args)
+        assert rc == -1, (fn.__name__, rc)          # FGT_ERR_ARG
+        assert needle in L.fgt_last_error().decode(), (fn.__name__, L.fgt_last_error())
+    assert L.fgt_poisson_graph_destroy(None) == 0   # destroying nothing is not an error
+    with pytest.raises(RuntimeError, match="fgt_plane_max"):
+        lib.check(L.fgt_plane_max(None, 1, 16, None, None), "fgt_plane_max")
