@@ -13,12 +13,31 @@ itself is verified against a full run of the unmodified reference driver (tests/
 There is no CPU fallback in this module: GpuBackend raises without a CUDA device.
 """
 import argparse
+import os
+from concurrent.futures import ThreadPoolExecutor
 
 import cv2
 import numpy as np
 import scipy.ndimage
 import torch
 import torch.nn.functional as F
+
+HOST_THREADS = max(1, min(8, os.cpu_count() or 1))   # per-frame host work (TELEA, differences) runs on a small pool
+
+
+def _frame_major(n, h, w, c=None, dtype=np.float32):
+    """Zero array indexed [H,W,(C,)N] like the driver's clips but stored frame-major, so that a frame `a[..., i]` is
+    contiguous (the driver's own layout makes every per-frame operation a stride-N gather)."""
+    base = np.zeros((n, h, w) + (() if c is None else (c,)), dtype=dtype)
+    return np.moveaxis(base, 0, -1)
+
+
+def _per_frame(fn, n):
+    if HOST_THREADS == 1 or n == 1:
+        return [fn(i) for i in range(n)]
+    with ThreadPoolExecutor(max_workers=min(HOST_THREADS, n)) as pool:
+        return list(pool.map(fn, range(n)))
+
 
 DEFAULTS = dict(imgH=256, imgW=432, flow_mask_dilates=8, frame_dilates=0, consistencyThres=5.0, alpha=0.1,
                 Nonlocal=False, step=10, num_ref=-1, neighbor_stride=5, raft_iters=20)
@@ -91,7 +110,7 @@ def prepare_masks(masks_u8, args):
             m = scipy.ndimage.binary_dilation(m, iterations=args.frame_dilates)
         mask.append(m)
         dilated.append(gradient_mask(m))
-    st = lambda xs: np.stack(xs, -1).astype(bool)
+    st = lambda xs: np.moveaxis(np.stack(xs, 0).astype(bool), 0, -1)        # [H,W,N] view, frame-major storage
     return st(mask), st(dilated), st(flow_mask)
 
 
@@ -114,9 +133,10 @@ def prepare_gradients(video, mask, mask_dilated):
     """:583-614 — zero the hole (in place, like the driver), TELEA-inpaint it for a plausible initialisation, take
     forward differences and zero them wherever they touch the hole. video [H,W,3,N] float32 (BGR, 0..1)."""
     H, W, _, N = video.shape
-    gx = np.zeros((H, W, 3, N), dtype=np.float32)      # last column / row stay zero (:601-606)
-    gy = np.zeros((H, W, 3, N), dtype=np.float32)
-    for i in range(N):
+    gx = _frame_major(N, H, W, 3)                      # last column / row stay zero (:601-606)
+    gy = _frame_major(N, H, W, 3)
+
+    def one(i):
         img = video[:, :, :, i]
         img[mask[:, :, i], :] = 0
         img = cv2.inpaint((img * 255).astype(np.uint8), mask[:, :, i].astype(np.uint8), 3, cv2.INPAINT_TELEA).astype(np.float32) / 255.0
@@ -124,6 +144,8 @@ def prepare_gradients(video, mask, mask_dilated):
         gy[:H - 1, :, :, i] = np.diff(img, axis=0)
         gx[mask_dilated[:, :, i], :, i] = 0
         gy[mask_dilated[:, :, i], :, i] = 0
+
+    _per_frame(one, N)                                  # frames are independent; each task writes its own frame
     return gx, gy
 
 
@@ -132,18 +154,21 @@ def blend_frames(backend, video, gx, gy, mask, mask_gradient):
     (all of them in one batch), TELEA-inpaint what the blend could not reach, mark it green in the frames handed to
     the transformer. Updates `video` and `mask` in place like the driver; returns the list of frames."""
     H, W, _, N = video.shape
-    for i in range(N):
+
+    def fill(i):
         mask_gradient[:, :, i] = scipy.ndimage.binary_fill_holes(mask_gradient[:, :, i]).astype(bool)
+
+    _per_frame(fill, N)
     todo = [i for i in range(N) if mask[:, :, i].sum() > 0]
     blends = backend.poisson_frames([video[:, :, :, i] for i in todo], [gx[:, 0:W - 1, :, i] for i in todo],
                                     [gy[0:H - 1, :, :, i] for i in todo], [mask[:, :, i] for i in todo],
                                     [mask_gradient[:, :, i] for i in todo]) if todo else []
-    out = []
-    for i in range(N):
-        if i not in todo:
-            out.append(video[:, :, :, i])
-            continue
-        blend, unfilled = blends[todo.index(i)]
+    slot = {i: k for k, i in enumerate(todo)}
+
+    def finish(i):
+        if i not in slot:
+            return video[:, :, :, i]
+        blend, unfilled = blends[slot[i]]
         blend = np.clip(blend, 0, 1.0)
         tmp = cv2.inpaint((blend * 255).astype(np.uint8), unfilled.astype(np.uint8), 3, cv2.INPAINT_TELEA).astype(np.float32) / 255.0
         blend[unfilled, :] = tmp[unfilled, :]
@@ -151,8 +176,9 @@ def blend_frames(backend, video, gx, gy, mask, mask_gradient):
         mask[:, :, i] = unfilled
         shown = blend.copy()
         shown[unfilled, :] = [0, 1.0, 0]          # green = not filled by propagation (:678-679); masked out for the model
-        out.append(shown)
-    return out
+        return shown
+
+    return _per_frame(finish, N)
 
 
 # ------------------------------------------------------------------------------------------------ backend
@@ -337,8 +363,9 @@ def video_inpainting(frames_u8, masks_u8, backend, args=None, num_flows=3, flow_
     video, video_flow = load_clip(frames_u8, args)
     flow_f = compute_flows(backend, video_flow, args, "forward")
     flow_b = compute_flows(backend, video_flow, args, "backward")
-    video = np.ascontiguousarray(video.permute(2, 3, 1, 0).numpy()[:, :, ::-1, :]) / 255.0       # [H,W,3(BGR),N], :499-501
-    video = video.astype(np.float32)
+    # [H,W,3(BGR),N] in 0..1 (:499-501), stored frame-major so that every per-frame view is contiguous
+    video = np.moveaxis(np.ascontiguousarray(video.permute(0, 2, 3, 1).numpy()[..., ::-1]) / 255.0, 0, -1)
+    assert video.dtype == np.float32
     mask, mask_dilated, flow_mask = prepare_masks(masks_u8, args)
     done_f = complete_flows(backend, flow_f, flow_mask, "forward", num_flows, flow_interval)
     done_b = complete_flows(backend, flow_b, flow_mask, "backward", num_flows, flow_interval)
