@@ -224,8 +224,17 @@ __device__ __forceinline__ void epi_chunk(const EpiArgs& e, const uint32_t (&raw
   }
 }
 
-template <int kExt>
+// Debugging aid (fgt_debug_gemm_trace): clock64 timeline of one CTA, [role 0 producer | 1 MMA | 2 epilogue][local tile
+// 0..63][4 slots]. Only the kTrace instantiation reads these; the production instantiations are unchanged by it.
+__device__ long long* g_gemm_trace = nullptr;
+__device__ int g_gemm_trace_cta = 0;
+
+template <int kExt, int kTrace = 0>
 __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  long long* trace = nullptr;
+  if (kTrace) trace = (static_cast<int>(blockIdx.x) == g_gemm_trace_cta) ? g_gemm_trace : nullptr;
+#define FGT_GTRACE(role, lt, slot) \
+  if (kTrace && trace && (lt) < 64) trace[((role) * 64 + (lt)) * 4 + (slot)] = clock64()
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms.
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -275,7 +284,8 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = 2u * static_cast<uint32_t>(p.a_rows) * 128u + 2u * b_plane_bytes;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int plt = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++plt) {
         const int nt = tile % p.n_tiles;
         const int mt = tile / p.n_tiles;
         const int z = mt / tiles_per_z;
@@ -286,6 +296,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
         const int n0 = nt * p.bn;
         const int group = n0 / p.cout_per_group;
         int kidx = 0;
+        FGT_GTRACE(0, plt, 0);
         for (int t = 0; t < p.num_taps; ++t) {
           const TapDesc tap = p.taps[t];
           for (int sgi = 0; sgi < p.num_segs; ++sgi) {
@@ -294,6 +305,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
             const int c0 = sg.c_base + group * sg.c_per_group;
             for (int ch = 0; ch < sg.chunks; ++ch, ++kidx) {
               mbar_wait(empty_bar(stage), phase ^ 1u);
+              if (kTrace && kidx == 0) { FGT_GTRACE(0, plt, 1); }
               const uint32_t sa = smem_base + stage * stage_bytes;
               const uint32_t sb = sa + 2u * kAPlaneBytes;
               const uint32_t fb = full_bar(stage);
@@ -307,6 +319,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
             }
           }
         }
+        FGT_GTRACE(0, plt, 2);
       }
     }
     __syncwarp();
@@ -320,12 +333,15 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
         const int buf = lt & 1;
         const uint32_t aph = (lt >> 1) & 1u;
+        FGT_GTRACE(1, lt, 0);
         mbar_wait(acce_bar(buf), aph ^ 1u);
         tc_fence_after();
+        FGT_GTRACE(1, lt, 1);
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(buf * p.bn_p2);
         for (int it = 0; it < p.k_iters; ++it) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
+          if (kTrace && it == 0) { FGT_GTRACE(1, lt, 2); }
           const uint32_t sa = smem_base + stage * stage_bytes;
           const uint32_t sb = sa + 2u * kAPlaneBytes;
           const uint64_t a_hi = umma_desc_sw128(sa);
@@ -343,6 +359,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(accf_bar(buf));
+        FGT_GTRACE(1, lt, 3);
       }
     }
     __syncwarp();
@@ -398,8 +415,10 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
         sbias[c] = (p.bias && n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.f;
       asm volatile("bar.sync 1, 128;\n" ::: "memory");
 
+      if (kTrace && warp == 2 && lane == 0) { FGT_GTRACE(2, lt, 0); }
       mbar_wait(accf_bar(buf), aph);
       tc_fence_after();
+      if (kTrace && warp == 2 && lane == 0) { FGT_GTRACE(2, lt, 1); }
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(buf * e_bn_p2);
       if ((e_bn & 31) == 0) {
@@ -420,8 +439,10 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acce_bar(buf));
+      if (kTrace && warp == 2 && lane == 0) { FGT_GTRACE(2, lt, 2); }
     }
   }
+#undef FGT_GTRACE
 
   tc_fence_before();
   __syncthreads();
@@ -438,6 +459,8 @@ static int next_pow2_ge32(int v) {
 }
 
 static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+static bool g_gemm_trace_on = false;  // debugging aid, see fgt_debug_gemm_trace()
 
 int gemm_tc_launch(const FgtGemmDesc& d, cudaStream_t stream) {
   FGT_REQUIRE(d.num_segs >= 1 && d.num_segs <= 2, FGT_ERR_ARG, "gemm_tc: num_segs=%d", d.num_segs);
@@ -571,6 +594,7 @@ int gemm_tc_launch(const FgtGemmDesc& d, cudaStream_t stream) {
   if (!attr_set) {
     FGT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     FGT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FGT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const bool ext = d.aux_mode == FGT_AUX_ADD_PRE || d.aux_mode == FGT_AUX_ADD_RELU || d.aux_mode == FGT_AUX_GRU ||
@@ -583,6 +607,7 @@ int gemm_tc_launch(const FgtGemmDesc& d, cudaStream_t stream) {
   if (grid > p.total_tiles) grid = p.total_tiles;
   FGT_REQUIRE(grid >= 1, FGT_ERR_ARG, "gemm_tc: empty problem");
   if (ext) launch_k(gemm_tc_kernel<1>, dim3(grid), dim3(192), smem, stream, p);
+  else if (g_gemm_trace_on) launch_k(gemm_tc_kernel<0, 1>, dim3(grid), dim3(192), smem, stream, p);
   else launch_k(gemm_tc_kernel<0>, dim3(grid), dim3(192), smem, stream, p);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;
@@ -593,4 +618,16 @@ int gemm_tc_launch(const FgtGemmDesc& d, cudaStream_t stream) {
 extern "C" int fgt_gemm_tc(const FgtGemmDesc* desc, fgt_stream_t stream) {
   if (!desc) return fgt::set_err(FGT_ERR_ARG, "fgt_gemm_tc: null desc");
   return fgt::gemm_tc_launch(*desc, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// Debugging aid (not part of the product interface, like fgt_debug_flash_trace): while buf != NULL, common-epilogue
+// launches use the traced instantiation and CTA `cta` writes its clock64 timeline into buf
+// ([3 roles][64 local tiles][4 slots] int64, device memory): producer {tile start, first stage slot free, last load
+// issued}, MMA {tile start, accumulator buffer free, first operands landed, last MMA committed}, epilogue {tile start,
+// accumulator complete, stores issued}.
+extern "C" int fgt_debug_gemm_trace(long long* buf, int cta) {
+  FGT_CUDA(cudaMemcpyToSymbol(fgt::g_gemm_trace, &buf, sizeof(buf)));
+  FGT_CUDA(cudaMemcpyToSymbol(fgt::g_gemm_trace_cta, &cta, sizeof(cta)));
+  fgt::g_gemm_trace_on = buf != nullptr;
+  return FGT_OK;
 }
