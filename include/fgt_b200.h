@@ -139,6 +139,10 @@ int fgt_attention(const FgtAttnDesc* desc, fgt_stream_t stream);
 /* Debug aid (not on the data path): with a device buffer of 3*64*8 int64, subsequent fgt_attention
  * launches record clock64() of CTA (0,0,0) per role (TMA / MMA / softmax) and key tile; NULL disables. */
 int fgt_debug_flash_trace(long long* device_buf);
+/* Debug aid (not on the data path): with a device buffer of 3*64*4 int64, subsequent common-epilogue fgt_gemm_tc
+ * launches use a traced instantiation in which CTA `cta` records clock64() per role (TMA producer / MMA issuer /
+ * epilogue) and local tile (see tools/trace_gemm.py for the slots); NULL disables. */
+int fgt_debug_gemm_trace(long long* device_buf, int cta);
 
 /* ------------------------------------------------------------------------------------------
  * HBM-bound helpers (coalesced / vectorised CUDA-core kernels). "split" outputs are split-bf16.
