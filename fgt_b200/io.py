@@ -61,12 +61,13 @@ def read_frames(directory):
     return [np.array(Image.open(f).convert("RGB")).astype(np.uint8) for f in files]
 
 
-def read_masks(directory):
-    """Greyscale masks as the driver loads them (Image.open(f).convert('L'), :543)."""
+def read_masks(directory, rgb=False):
+    """Greyscale masks as the driver loads them (Image.open(f).convert('L'), :543); rgb=True keeps the file's own
+    channels, which is what the watermark mode multiplies the frames with (:466-471)."""
     files = list_images(directory)
     if not files:
         raise FileNotFoundError(f"no *.png / *.jpg masks in {directory}")
-    return [np.array(Image.open(f).convert("L")) for f in files]
+    return [np.array(Image.open(f)) if rgb else np.array(Image.open(f).convert("L")) for f in files]
 
 
 def write_frames(outdir, frames, mp4=True, fps=30):

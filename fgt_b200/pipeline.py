@@ -39,8 +39,9 @@ def _per_frame(fn, n):
         return list(pool.map(fn, range(n)))
 
 
-DEFAULTS = dict(imgH=256, imgW=432, flow_mask_dilates=8, frame_dilates=0, consistencyThres=5.0, alpha=0.1,
-                Nonlocal=False, step=10, num_ref=-1, neighbor_stride=5, raft_iters=20)
+DEFAULTS = dict(mode="object_removal", imgH=256, imgW=432, flow_mask_dilates=8, frame_dilates=0, consistencyThres=5.0,
+                alpha=0.1, Nonlocal=False, step=10, num_ref=-1, neighbor_stride=5, raft_iters=20, H_scale=2.0, W_scale=2.0)
+MODES = ("object_removal", "watermark_removal", "video_extrapolation")
 
 
 def make_args(**kw):
@@ -70,17 +71,49 @@ def gradient_mask(mask):
 
 
 # ------------------------------------------------------------------------------------------------ stages
-def load_clip(frames_u8, args):
-    """:470-490 — uint8 RGB frames [N,h,w,3] -> (video [N,3,imgH,imgW], video_flow [N,3,flowH,flowW]) float32 0..255.
-    RAFT sees frames at twice the working resolution when imgH < 350 (:440-443)."""
+def load_clip(frames_u8, args, masks_u8=None):
+    """:452-497 — uint8 RGB frames [N,h,w,3] -> (video [N,3,imgH,imgW], video_flow [N,3,flowH,flowW]) float32 0..255.
+    RAFT sees frames at twice the working resolution when imgH < 350 (:440-443). In watermark_removal mode the frames
+    are multiplied by (1 - mask) at their native size before any resizing (:454-473; masks [N,h,w] or [N,h,w,3],
+    non-zero = watermark)."""
     flow_hw = (args.imgH * 2, args.imgW * 2) if args.imgH < 350 else (args.imgH, args.imgW)
     video, video_flow = [], []
-    for fr in frames_u8:
+    for k, fr in enumerate(frames_u8):
         t = torch.from_numpy(np.ascontiguousarray(fr).astype(np.uint8)).permute(2, 0, 1).float().unsqueeze(0)
+        if masks_u8 is not None:
+            m = np.asarray(masks_u8[k]).astype(np.uint8)
+            m = torch.from_numpy(np.ascontiguousarray(m if m.ndim == 3 else m[..., None])).permute(2, 0, 1).float().unsqueeze(0)
+            m[m > 0] = 1
+            t = t * (1 - m)
         t = F.interpolate(t, size=(args.imgH, args.imgW), mode="bilinear", align_corners=False)
         video.append(t)
         video_flow.append(F.interpolate(t, size=flow_hw, mode="bilinear", align_corners=False))
     return torch.cat(video, 0), torch.cat(video_flow, 0)
+
+
+def extrapolate(video, flow_f, flow_b, h_scale, w_scale):
+    """extrapolation (:286-335): a canvas H_scale x W_scale as large (rounded down to multiples of 4) with the clip in
+    the middle; the border is the hole. The frames are TELEA-inpainted into the border right away, the flows are
+    zero there. Returns (video, flow_f, flow_b, flow_mask [H',W'] bool, mask_dilated [H',W'] bool)."""
+    H, W, _, N = video.shape
+    He, We = int(h_scale * H), int(w_scale * W)
+    He, We = He - He % 4, We - We % 4
+    y0, x0 = int((He - H) / 2), int((We - W) / 2)
+    flow_mask = np.ones((He, We), dtype=bool)
+    flow_mask[y0:y0 + H, x0:x0 + W] = False
+    big = _frame_major(N, He, We, 3)
+    big[y0:y0 + H, x0:x0 + W] = video
+
+    def fill(i):
+        big[:, :, :, i] = cv2.inpaint((big[:, :, :, i] * 255).astype(np.uint8), flow_mask.astype(np.uint8), 3,
+                                      cv2.INPAINT_TELEA).astype(np.float32) / 255.0
+
+    _per_frame(fill, N)
+    ff = np.zeros((He, We, 2, N - 1), dtype=np.float32)
+    fb = np.zeros((He, We, 2, N - 1), dtype=np.float32)
+    ff[y0:y0 + H, x0:x0 + W] = flow_f
+    fb[y0:y0 + H, x0:x0 + W] = flow_b
+    return big, ff, fb, flow_mask, gradient_mask(flow_mask)
 
 
 def compute_flows(backend, video_flow, args, mode):
@@ -104,6 +137,10 @@ def prepare_masks(masks_u8, args):
     """:539-567 — per-frame uint8 masks [N,h,w] (non-zero = hole) -> (mask, mask_dilated, flow_mask) bool [H,W,N]."""
     mask, dilated, flow_mask = [], [], []
     for m in masks_u8:
+        m = np.asarray(m)
+        if m.ndim == 3:                                   # a colour mask file: the driver reads it with .convert("L") (:543)
+            from PIL import Image
+            m = np.array(Image.fromarray(m.astype(np.uint8)).convert("L"))
         m = cv2.resize(np.ascontiguousarray(m).astype(np.uint8), dsize=(args.imgW, args.imgH), interpolation=cv2.INTER_NEAREST)
         flow_mask.append(scipy.ndimage.binary_dilation(m, iterations=args.flow_mask_dilates) if args.flow_mask_dilates > 0 else m)
         if args.frame_dilates > 0:
@@ -356,17 +393,27 @@ class ShardedBackend:
 
 # ------------------------------------------------------------------------------------------------ driver
 def video_inpainting(frames_u8, masks_u8, backend, args=None, num_flows=3, flow_interval=3, return_stages=False):
-    """Object removal on a clip: frames_u8 [N,h,w,3] RGB uint8 (the PNGs the driver reads), masks_u8 [N,h,w]
-    (non-zero = remove) -> list of N uint8 RGB frames [imgH,imgW,3] (what the driver writes to result.mp4).
-    `args`: make_args(...); num_flows / flow_interval are the LAFC config entries the driver reads (:352)."""
+    """The driver on arrays: frames_u8 [N,h,w,3] RGB uint8 (the PNGs the driver reads), masks_u8 [N,h,w] (non-zero =
+    remove; ignored by video_extrapolation) -> list of N uint8 RGB frames (what the driver writes to result.mp4).
+    `args`: make_args(...), `args.mode` one of object_removal (default), watermark_removal (frames are masked before
+    resizing, :454-473), video_extrapolation (the clip is placed in a larger canvas whose border is inpainted,
+    :516-537); num_flows / flow_interval are the LAFC config entries the driver reads (:352)."""
     args = args or make_args()
-    video, video_flow = load_clip(frames_u8, args)
+    if args.mode not in MODES:
+        raise ValueError(f"Accepted modes: {MODES}, but input is {args.mode}")
+    video, video_flow = load_clip(frames_u8, args, masks_u8 if args.mode == "watermark_removal" else None)
     flow_f = compute_flows(backend, video_flow, args, "forward")
     flow_b = compute_flows(backend, video_flow, args, "backward")
     # [H,W,3(BGR),N] in 0..1 (:499-501), stored frame-major so that every per-frame view is contiguous
     video = np.moveaxis(np.ascontiguousarray(video.permute(0, 2, 3, 1).numpy()[..., ::-1]) / 255.0, 0, -1)
     assert video.dtype == np.float32
-    mask, mask_dilated, flow_mask = prepare_masks(masks_u8, args)
+    if args.mode == "video_extrapolation":
+        N = video.shape[3]
+        video, flow_f, flow_b, fm2, md2 = extrapolate(video, flow_f, flow_b, args.H_scale, args.W_scale)
+        tile = lambda m: np.moveaxis(np.repeat(m[None], N, 0), 0, -1)           # the same mask for every frame (:531-535)
+        mask, mask_dilated, flow_mask = tile(fm2), tile(md2), tile(fm2)
+    else:
+        mask, mask_dilated, flow_mask = prepare_masks(masks_u8, args)
     done_f = complete_flows(backend, flow_f, flow_mask, "forward", num_flows, flow_interval)
     done_b = complete_flows(backend, flow_b, flow_mask, "backward", num_flows, flow_interval)
     gx, gy = prepare_gradients(video, mask, mask_dilated)
@@ -413,25 +460,28 @@ def load_models(raft_model, lafc_ckpts, fgt_ckpts, device):
 
 
 def main(argv=None):
-    """`python -m fgt_b200.pipeline --path frames/ --path_mask masks/ --outroot out/ ...` — the driver's command line
-    for object removal (:764-855; options of the other modes and the visualisation switches are not offered)."""
+    """`python -m fgt_b200.pipeline --path frames/ --path_mask masks/ --outroot out/ [--mode ...] ...` — the driver's
+    command line (:764-855; the visualisation switches are not offered)."""
     from . import io as IO
     ap = argparse.ArgumentParser(description=main.__doc__)
     ap.add_argument("--path", required=True, help="directory of *.png / *.jpg frames")
-    ap.add_argument("--path_mask", required=True, help="directory of masks (non-zero = remove)")
+    ap.add_argument("--path_mask", default=None, help="directory of masks (non-zero = remove); not needed for video_extrapolation")
     ap.add_argument("--outroot", required=True, help="output directory (frames/%%05d.png, result.mp4)")
     ap.add_argument("--raft_model", default="../LAFC/flowCheckPoint/raft-things.pth")
     ap.add_argument("--lafc_ckpts", default="../LAFC/checkpoint")
     ap.add_argument("--fgt_ckpts", default="../FGT/checkpoint")
     ap.add_argument("--gpu", type=int, default=0)
     for k, v in DEFAULTS.items():
-        if k not in ("Nonlocal", "raft_iters"):
+        if k == "mode":
+            ap.add_argument("--mode", default=v, choices=list(MODES))
+        elif k not in ("Nonlocal", "raft_iters"):
             ap.add_argument("--" + k, type=type(v), default=v)
     ns = ap.parse_args(argv)
     dev = torch.device("cuda", ns.gpu)
     backend, lafc_cfg = load_models(ns.raft_model, ns.lafc_ckpts, ns.fgt_ckpts, dev)
     args = make_args(**{k: getattr(ns, k) for k in DEFAULTS if hasattr(ns, k)})
-    frames, masks = IO.read_frames(ns.path), IO.read_masks(ns.path_mask)
+    frames = IO.read_frames(ns.path)
+    masks = IO.read_masks(ns.path_mask, rgb=ns.mode == "watermark_removal") if ns.mode != "video_extrapolation" else [None] * len(frames)
     if len(frames) != len(masks):
         raise ValueError(f"{len(frames)} frames but {len(masks)} masks")
     comp = video_inpainting(frames, masks, backend, args, lafc_cfg["num_flows"], lafc_cfg["flow_interval"])

@@ -41,11 +41,28 @@ CAPTURE = {}
 # (0.25 / 0.25 / 0.5 averaging), a reference frame outside the neighbourhood, no frame dilation (uint8 mask branch,
 # :556-561), other seeds. Only the final frames and the propagation mask are stored (pipeline12.npz).
 SECOND = dict(N=12, clip_seed=9, fgt_seed=41, lafc_seed=42, raft_seed=43, flow_mask_dilates=2, frame_dilates=0)
+# other driver modes (--watermark / --extrapolation): 7 frames; watermark: RGB mask files multiplied into the frames before
+# resizing; extrapolation: 64x96 clip on an 80x120 canvas (H_scale = W_scale = 1.25; RAFT needs >= 128 px on its
+# short side or its coarsest correlation level degenerates to one row and the reference divides by zero). Stored like
+# the second case.
+MODES = dict(watermark=dict(mode="watermark_removal", out="pipeline_watermark", clip_seed=13, fgt_seed=51, lafc_seed=52,
+                            raft_seed=53, flow_mask_dilates=2, frame_dilates=0, consistencyThres=1.0),
+             extrapolation=dict(mode="video_extrapolation", out="pipeline_extrapolation", clip_seed=14, fgt_seed=61,
+                                lafc_seed=62, raft_seed=63, flow_mask_dilates=0, frame_dilates=0, consistencyThres=5.0,
+                                H=64, W=96, scale=1.25, canvas=(80, 120)))
 
 
-def main(second=False):
-    global N
+def main(second=False, other=None):
+    global N, H, W
     cs, fs, ls, rs, fmd, fd = 5, 31, 32, 33, 3, 1
+    mode, thres, scale, cfg_hw = "object_removal", 5.0, 2.0, None
+    if other:
+        o = MODES[other]
+        mode, thres = o["mode"], o["consistencyThres"]
+        cs, fs, ls, rs, fmd, fd = o["clip_seed"], o["fgt_seed"], o["lafc_seed"], o["raft_seed"], o["flow_mask_dilates"], o["frame_dilates"]
+        if "scale" in o:
+            scale, cfg_hw = o["scale"], o["canvas"]       # the FGT checkpoint is configured for the canvas size
+            H, W = o["H"], o["W"]
     if second:
         N = SECOND["N"]
         cs, fs, ls, rs = SECOND["clip_seed"], SECOND["fgt_seed"], SECOND["lafc_seed"], SECOND["raft_seed"]
@@ -64,9 +81,9 @@ def main(second=False):
             os.makedirs(os.path.join(tmp, d))
         for i, (fr, m) in enumerate(zip(frames, masks)):
             Image.fromarray(fr).save(os.path.join(tmp, "frames", "%05d.png" % i))
-            Image.fromarray(m).save(os.path.join(tmp, "masks", "%05d.png" % i))
+            Image.fromarray(np.repeat(m[..., None], 3, -1) if mode == "watermark_removal" else m).save(os.path.join(tmp, "masks", "%05d.png" % i))
         cfg = dict(synth.CFG_A)
-        cfg["input_resolution"] = (H, W)
+        cfg["input_resolution"] = cfg_hw or (H, W)
         fgt_sd = synth.make_state_dict(synth.fgt_param_shapes(cfg), seed=fs)
         torch.save({"model_state_dict": fgt_sd}, os.path.join(tmp, "fgt_ckpt", "fgt.tar"))
         ycfg = {k: (list(v) if isinstance(v, tuple) else v) for k, v in cfg.items()}
@@ -81,13 +98,13 @@ def main(second=False):
         torch.save({"module." + k: v for k, v in raft_sd.items()}, os.path.join(tmp, "raft.pth"))
         opt = os.path.join(tmp, "opt.yaml")
         with open(opt, "w") as fh:
-            yaml.safe_dump(dict(mode="object_removal", consistencyThres=5, alpha=0.1, flow_mask_dilates=fmd, frame_dilates=fd), fh)
+            yaml.safe_dump(dict(mode=mode, consistencyThres=thres, alpha=0.1, flow_mask_dilates=fmd, frame_dilates=fd), fh)
         args = argparse.Namespace(
-            opt=opt, mode="object_removal", path=os.path.join(tmp, "frames"), path_mask=os.path.join(tmp, "masks"),
-            outroot=os.path.join(tmp, "out"), consistencyThres=5.0, alpha=0.1, Nonlocal=False,
+            opt=opt, mode=mode, path=os.path.join(tmp, "frames"), path_mask=os.path.join(tmp, "masks"),
+            outroot=os.path.join(tmp, "out"), consistencyThres=thres, alpha=0.1, Nonlocal=False,
             raft_model=os.path.join(tmp, "raft.pth"), small=False, mixed_precision=False,
             alternate_corr=False, lafc_ckpts=os.path.join(tmp, "lafc_ckpt"), fgt_ckpts=os.path.join(tmp, "fgt_ckpt"),
-            H_scale=2, W_scale=2, imgH=H, imgW=W, flow_mask_dilates=fmd, frame_dilates=fd, gpu=0, step=10, num_ref=-1,
+            H_scale=scale, W_scale=scale, imgH=H, imgW=W, flow_mask_dilates=fmd, frame_dilates=fd, gpu=0, step=10, num_ref=-1,
             neighbor_stride=5, vis_flows=False, vis_completed_flows=False, vis_prop=False, vis_frame=False)
 
         # hooks: record, then call the unmodified function
@@ -131,16 +148,17 @@ def main(second=False):
 
     import cv2
     import scipy
-    meta = dict(H=H, W=W, N=N, fgt_seed=fs, lafc_seed=ls, raft_seed=rs, clip_seed=cs, flow_mask_dilates=fmd, frame_dilates=fd, torch=torch.__version__, numpy=np.__version__,
+    meta = dict(mode=mode, consistencyThres=thres, scale=scale, cfg_hw=list(cfg_hw or (H, W)), H=H, W=W, N=N, fgt_seed=fs, lafc_seed=ls, raft_seed=rs, clip_seed=cs, flow_mask_dilates=fmd, frame_dilates=fd, torch=torch.__version__, numpy=np.__version__,
                 scipy=scipy.__version__, cv2=cv2.__version__)
     frame_blends, mask, flow_f = t_calls            # the three near="t" conversions of the FGT stage, in order
     comp = np.stack(CAPTURE["comp_frames"])
-    assert frame_blends.shape == (N, H, W, 3) and mask.shape == (N, H, W, 1) and flow_f.shape == (N, H, W, 2)
-    assert comp.shape == (N, H, W, 3) and comp.dtype == np.uint8
-    if second:
-        np.savez_compressed(os.path.join(HERE, "pipeline12.npz"), meta=np.array(repr(meta)), comp=comp,
+    oh, ow = comp.shape[1:3]
+    assert frame_blends.shape == (N, oh, ow, 3) and mask.shape == (N, oh, ow, 1) and flow_f.shape == (N, oh, ow, 2)
+    assert comp.dtype == np.uint8 and ((oh, ow) == (H, W) or mode == "video_extrapolation")
+    if second or other:
+        np.savez_compressed(os.path.join(HERE, (MODES[other]["out"] if other else "pipeline12") + ".npz"), meta=np.array(repr(meta)), comp=comp,
                             mask_gradient=np.packbits(stages["mask_gradient"]), mask_final=np.packbits(mask.astype(bool)))
-        print("pipeline12 saved: comp mean", comp.mean(), "final holes", int(mask.sum()))
+        print(MODES[other]["out"] if other else "pipeline12", "saved: comp", comp.shape, "mean", comp.mean(), "final holes", int(mask.sum()))
         return
     # frame_blends as recorded are already RGB (the driver flips in place before np2tensor, :688-689)
     np.savez_compressed(os.path.join(HERE, "pipeline_clip.npz"), meta=np.array(repr(meta)),
@@ -162,4 +180,5 @@ def main(second=False):
 
 
 if __name__ == "__main__":
-    main(second="--second" in sys.argv)
+    main(second="--second" in sys.argv,
+         other="watermark" if "--watermark" in sys.argv else ("extrapolation" if "--extrapolation" in sys.argv else None))

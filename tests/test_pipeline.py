@@ -213,3 +213,36 @@ def test_pipeline_glue_second_reference_run_12_frames():
     assert np.array_equal(np.moveaxis(stages["mask"], -1, 0).reshape(-1), bits("mask_final").astype(bool))
     diff = np.abs(np.stack(comp).astype(np.int16) - g["comp"].astype(np.int16))
     assert diff.max() <= 1 and (diff != 0).mean() < 1e-3, (diff.max(), (diff != 0).mean())
+
+
+@pytest.mark.parametrize("name", ["pipeline_watermark", "pipeline_extrapolation"])
+def test_pipeline_other_driver_modes_match_reference_runs(name):
+    """The driver's two other modes, each pinned by its own full run of the unmodified reference driver: watermark
+    removal (RGB mask files multiplied into the frames before any resizing, consistencyThres 1) and video extrapolation
+    (a 64x96 clip on an 80x120 canvas whose TELEA-initialised border is the hole; FGT runs at the canvas size)."""
+    from oracle.pipeline_oracle import OracleBackend
+    g = load_golden(name)
+    m = g["meta"]
+    frames, masks = synth.pipeline_clip(seed=m["clip_seed"], N=m["N"], H=m["H"], W=m["W"])
+    if m["mode"] == "watermark_removal":
+        masks = [np.repeat(x[..., None], 3, -1) for x in masks]           # colour mask files, as the driver expects there
+    args = PL.make_args(mode=m["mode"], imgH=m["H"], imgW=m["W"], flow_mask_dilates=m["flow_mask_dilates"],
+                        frame_dilates=m["frame_dilates"], consistencyThres=m["consistencyThres"], H_scale=m["scale"],
+                        W_scale=m["scale"])
+    cfg = dict(synth.CFG_A)
+    cfg["input_resolution"] = tuple(m["cfg_hw"])
+    be = OracleBackend(synth.raft_state_dict(seed=m["raft_seed"]),
+                       O.strip_net(synth.make_state_dict(synth.lafc_param_shapes(synth.CFG_LAFC), seed=m["lafc_seed"])),
+                       O.strip_net(synth.make_state_dict(synth.fgt_param_shapes(cfg), seed=m["fgt_seed"])))
+    comp, stages = PL.video_inpainting(frames, None if m["mode"] == "video_extrapolation" else masks, be, args,
+                                       return_stages=True)
+    comp = np.stack(comp)
+    assert comp.shape == g["comp"].shape
+    n = comp.shape[0] * comp.shape[1] * comp.shape[2]
+    bits = lambda k: np.unpackbits(g[k])[:n].astype(bool)
+    assert np.array_equal(np.asarray(stages["mask_gradient"], bool).reshape(-1), bits("mask_gradient"))
+    assert np.array_equal(np.moveaxis(stages["mask"], -1, 0).reshape(-1), bits("mask_final"))
+    diff = np.abs(comp.astype(np.int16) - g["comp"].astype(np.int16))
+    assert diff.max() <= 1 and (diff != 0).mean() < 1e-3, (diff.max(), (diff != 0).mean())
+    with pytest.raises(ValueError):
+        PL.video_inpainting(frames, masks, be, PL.make_args(mode="colourise"))
