@@ -263,8 +263,11 @@ class GpuBackend:
     def poisson_frames(self, trg, gx, gy, hole, gmask):
         from .poisson import poisson_blend_batch
         st = lambda xs: np.ascontiguousarray(np.stack(xs, 0))
-        out, unf = poisson_blend_batch(st(trg), st(gx), st(gy), st(hole), st(gmask), device=self.dev)
-        out, unf = out.cpu().numpy(), unf.cpu().numpy()
+        trg = st(trg)
+        out, unf = poisson_blend_batch(trg, st(gx), st(gy), st(hole), st(gmask), device=self.dev)
+        if trg.dtype == np.float32:      # every value of the blend is then a float32 (float64(float32(x)) in the hole, the
+            out = out.float()            # float32 target outside): half the bytes back over the bus, widened exactly on the host
+        out, unf = out.cpu().numpy().astype(np.float64), unf.cpu().numpy()
         return [(out[i], unf[i]) for i in range(out.shape[0])]
 
     def fgt_stage(self, frame_blends, mask, flow_f, step, num_ref, neighbor_stride):

@@ -44,7 +44,8 @@ def poisson_blend_batch(trg, gx, gy, hole, gmask=None, edge=None, device=None, r
     (+ per-system (istop, itn) int tensors [F,3] with return_info). use_graph: replay each chunk of iterations as one
     CUDA graph (default) or launch its kernels one by one."""
     dev = _dev(device)
-    t64 = lambda a: torch.as_tensor(np.ascontiguousarray(a) if not torch.is_tensor(a) else a).to(dev, torch.float64).contiguous()
+    # host arrays cross the bus in their own dtype (float32 in the driver) and are widened on the device (exact)
+    t64 = lambda a: torch.as_tensor(np.ascontiguousarray(a) if not torch.is_tensor(a) else a).to(dev).to(torch.float64).contiguous()
     trg, gx, gy = t64(trg), t64(gx), t64(gy)
     if trg.dim() != 4 or trg.shape[3] != 3:
         raise ValueError(f"poisson: target {tuple(trg.shape)} must be [F,H,W,3]")

@@ -55,3 +55,24 @@ def test_frame_directory_round_trip(tmp_path):
     assert masks[0].shape == (12, 16) and masks[0].dtype == np.uint8
     with pytest.raises(FileNotFoundError):
         IO.read_frames(str(tmp_path / "nothing"))
+
+
+def test_flow_extract_writes_the_reference_layout(tmp_path):
+    """tool/flow_extract.py's output tree, with a stand-in for RAFT (flow = mean colour difference, 2 channels)."""
+    import torch
+    from fgt_b200 import flow_extract as FE
+    rng = np.random.default_rng(1)
+    frames = [rng.integers(0, 256, (20, 30, 3), dtype=np.uint8) for _ in range(4)]
+
+    def fake_raft(a, b, iters):
+        d = (b - a).mean(1, keepdim=True)
+        return torch.cat([d, -d], 1).numpy()
+
+    fwd, bwd = FE.extract_video(frames, fake_raft, str(tmp_path / "vid"), width=32, height=24)
+    assert fwd.shape == (3, 24, 32, 2) and np.allclose(fwd, -bwd)
+    for mode, ref in (("forward_flo", fwd), ("backward_flo", bwd)):
+        files = sorted(os.listdir(tmp_path / "vid" / mode))
+        assert files == ["00000.flo", "00001.flo", "00002.flo"]
+        assert np.array_equal(IO.read_flo(str(tmp_path / "vid" / mode / files[1])), ref[1])
+    with pytest.raises(ValueError):
+        FE.extract_video(frames, fake_raft, str(tmp_path / "bad"), width=30, height=20)
