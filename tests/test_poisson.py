@@ -69,6 +69,41 @@ def test_oracle_operator_adjoint_and_duplicate_equations():
         assert np.array_equal(b[n, ys, xs], -b[m, qy, qx])
 
 
+def test_oracle_lsqr_equals_scipy_lsqr_on_the_assembled_system():
+    """Independent check of the restated solver: assemble the sparse system explicitly from the equation codes and run
+    the real scipy.sparse.linalg.lsqr (float64, default tolerances) on it — same stopping iteration, same istop, same
+    iterate as the matrix-free restatement (random ragged holes, gradient masks and edges)."""
+    from scipy import sparse
+    from scipy.sparse.linalg import lsqr as scipy_lsqr
+    rng = np.random.default_rng(7)
+    H, W = 26, 34
+    for trial in range(4):
+        hole = rng.random((H, W)) < (0.25, 0.5, 0.7, 0.4)[trial]
+        hole[8:18, 10:24] = True
+        gm = (rng.random((H, W)) < 0.15) & hole
+        edge = (rng.random((H, W)) < 0.05).astype(np.float32) if trial % 2 else np.zeros((H, W), np.float32)
+        trg = rng.random((H, W, 3)).astype(np.float32)
+        trg[hole] = 0
+        gx = rng.standard_normal((H, W - 1, 3)).astype(np.float32) * 0.1
+        gy = rng.standard_normal((H - 1, W, 3)).astype(np.float32) * 0.1
+        code = PO.equation_codes(hole, gm, edge)
+        b = PO.rhs(code, trg, gx.astype(np.float64), gy.astype(np.float64))
+        rows, cols, vals, rhs_v = [], [], [], []
+        for n in range(4):
+            ys, xs = np.nonzero((code >> n) & 1)
+            for y, x in zip(ys, xs):
+                r = len(rhs_v)
+                rows.append(r); cols.append(y * W + x); vals.append(1.0)
+                if (code[y, x] >> (4 + n)) & 1:
+                    rows.append(r); cols.append((y + PO.DY[n]) * W + x + PO.DX[n]); vals.append(-1.0)
+                rhs_v.append(b[n, y, x, 0])
+        A = sparse.csr_matrix((vals, (rows, cols)), shape=(len(rhs_v), H * W))
+        ref = scipy_lsqr(A, np.asarray(rhs_v))
+        x, istop, itn = PO.lsqr(code, b[..., 0])
+        assert (istop, itn) == (ref[1], ref[2]), (trial, istop, itn, ref[1], ref[2])
+        assert np.abs(x.reshape(-1) - ref[0]).max() < 1e-9
+
+
 def _advance(L, prev, k, bbk, aak, wwk, iter_lim):
     cur = np.zeros(16)
     step = np.zeros(6)
