@@ -46,6 +46,11 @@ def test_oracle_helpers_and_schedule():
         nb = list(range(max(0, f - 5), min(40, f + 6)))
         for num_ref in (-1, 2, 4):
             assert window_schedule(40, 5, 10, num_ref)[f // 5][2] == CO.get_ref_index(f, nb, 40, 10, num_ref)
+    for n in (1, 2, 7, 10, 12, 23, 80):                       # the product's schedule vs the oracle's own statement
+        for num_ref in (-1, 0, 2, 5):
+            for stride, step in ((5, 10), (3, 7)):
+                want = CO.windows(n, step, num_ref, stride)
+                assert [(nb, ref) for _, nb, ref in window_schedule(n, stride, step, num_ref)] == want, (n, num_ref, stride)
     fl = torch.randn(1, 3, 2, 4, 5)
     nf = CO.norm_flows(fl)
     assert torch.equal(nf[0, 1, 0], fl[0, 1, 0] / fl[0, 1, 0].max())
