@@ -1,7 +1,9 @@
 // Fused softmax(QK^T * scale) V on tcgen05 for FGT's two attentions (never materialises scores).
 //
 // One CTA = 128 query rows x one head (head dim 128). Keys are consumed in tiles of 64:
-//   warp 0 / 6 : TMA producers (K tiles / V^T tiles, two independent 3-deep rings)
+//   warp 0 / 6 : TMA producers (K tiles / V tiles, two independent 3-deep rings; V stays row-major
+//                [keys, d] and is consumed as an MN-major B operand, so the V projection GEMM stores
+//                through its vector path instead of a transposed scalar scatter)
 //   warp 1 / 7 : MMA issuers  (S_j = Q K_j^T / O += P_j V_j as two independent instruction streams,
 //                              3-term split-bf16, A operands in TMEM)
 //   warps 2..5 : softmax      (thread = query row: stages its Q row in TMEM once, then per key tile
@@ -22,7 +24,8 @@
 namespace fgt {
 
 constexpr int kKBlk = 64 * 128;       // one (plane, k-chunk) block of K: 64 keys x 128 B
-constexpr int kVBlk = 128 * 128;      // one plane of V^T: 128 dims x 64 keys (128 B)
+constexpr int kVBlk = 128 * 128;      // one plane of a V tile: two [64 keys x 64 dims (128 B)] halves of 8 KB
+constexpr int kVHalf = 64 * 128;
 constexpr int kKStage = 4 * kKBlk;    // 32 KB
 constexpr int kVStage = 2 * kVBlk;    // 32 KB
 constexpr int kStages = 3;            // K and V rings
@@ -140,7 +143,9 @@ __global__ void __launch_bounds__(256, 1) flash_kernel(const __grid_constant__ F
         FGT_TRACE(0, j, 1);
         mbar_expect_tx(v_full(s), kVStage);
         for (int pl = 0; pl < 2; ++pl)
-          tma_load_4d(sbase + kSmemV + s * kVStage + pl * kVBlk, &p.v_map, v_full(s), r0, head * 128, batch, pl);
+          for (int hf = 0; hf < 2; ++hf)
+            tma_load_4d(sbase + kSmemV + s * kVStage + pl * kVBlk + hf * kVHalf, &p.v_map, v_full(s),
+                        head * 128 + hf * 64, r0, batch, pl);
         if (++s == kStages) { s = 0; ph ^= 1u; }
       }
     }
@@ -185,7 +190,7 @@ __global__ void __launch_bounds__(256, 1) flash_kernel(const __grid_constant__ F
   } else if (warp == 7) {
     // ------------------------------------------------------------ O += P V issuer
     if (elect_one()) {
-      const uint32_t idesc_o = umma_idesc_bf16(128, 128);
+      const uint32_t idesc_o = umma_idesc_bf16(128, 128) | kIdescBMajorMN;  // B = V tile [keys, d]: d (N) contiguous
       int vs = 0;
       uint32_t vph = 0;
       for (int j = 0; j < n_tiles; ++j) {
@@ -197,11 +202,11 @@ __global__ void __launch_bounds__(256, 1) flash_kernel(const __grid_constant__ F
         tc_fence_after();
         const uint32_t d = tmem_base + kTmO;
         const uint32_t pa = tmem_base + kTmP + static_cast<uint32_t>(pb * 64);
-        const uint64_t b_hi = umma_desc_sw128(sbase + kSmemV + vs * kVStage);
-        const uint64_t b_lo = umma_desc_sw128(sbase + kSmemV + vs * kVStage + kVBlk);
+        const uint64_t b_hi = umma_desc_sw128_mn(sbase + kSmemV + vs * kVStage, kVHalf);
+        const uint64_t b_lo = umma_desc_sw128_mn(sbase + kSmemV + vs * kVStage + kVBlk, kVHalf);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint64_t ko = static_cast<uint64_t>(k * 2);
+          const uint64_t ko = static_cast<uint64_t>(k * 128);  // 16 keys = two 8-row swizzle atoms = 2048 B >> 4
           const uint32_t pc = static_cast<uint32_t>(k * 8);
           umma_bf16_ts(d, pa + 32u + pc, b_hi + ko, idesc_o, (j | k) != 0);  // P_lo * V_hi
           umma_bf16_ts(d, pa + pc, b_lo + ko, idesc_o, 1u);                  // P_hi * V_lo
@@ -374,9 +379,9 @@ static long long* g_flash_trace = nullptr;  // debugging aid, see fgt_debug_flas
 int attention_launch(const FgtAttnDesc& d, cudaStream_t stream) {
   FGT_REQUIRE(d.head_dim == 128, FGT_ERR_ARG, "attention: head_dim=%d (only 128 supported)", d.head_dim);
   FGT_REQUIRE(d.batches >= 1 && d.heads >= 1 && d.Lq >= 1 && d.Lk >= 1, FGT_ERR_ARG, "attention: empty problem");
-  FGT_REQUIRE(d.q_ld % 8 == 0 && d.k_ld % 8 == 0 && d.vt_ld % 8 == 0 && d.out_ld % 8 == 0, FGT_ERR_ARG,
+  FGT_REQUIRE(d.q_ld % 8 == 0 && d.k_ld % 8 == 0 && d.v_ld % 8 == 0 && d.out_ld % 8 == 0, FGT_ERR_ARG,
               "attention: leading dimensions must be multiples of 8 elements");
-  FGT_REQUIRE(d.q_batch_stride % 8 == 0 && d.k_batch_stride % 8 == 0 && d.vt_batch_stride % 8 == 0 &&
+  FGT_REQUIRE(d.q_batch_stride % 8 == 0 && d.k_batch_stride % 8 == 0 && d.v_batch_stride % 8 == 0 &&
                   d.out_batch_stride % 8 == 0 && d.out_plane % 8 == 0,
               FGT_ERR_ARG, "attention: batch strides must be multiples of 8 elements");
   FGT_REQUIRE(d.mode == 0 || d.mode == 1, FGT_ERR_ARG, "attention: mode=%d", d.mode);
@@ -399,12 +404,12 @@ int attention_launch(const FgtAttnDesc& d, cudaStream_t stream) {
     if (rc) return rc;
   }
   {
-    uint64_t dims[4] = {static_cast<uint64_t>(d.Lk_rows), hd, static_cast<uint64_t>(d.batches), 2};
-    uint64_t str[3] = {static_cast<uint64_t>(d.vt_ld) * 2, static_cast<uint64_t>(d.vt_batch_stride) * 2,
-                       static_cast<uint64_t>(d.vt_plane) * 2};
+    uint64_t dims[4] = {hd, static_cast<uint64_t>(d.Lk_rows), static_cast<uint64_t>(d.batches), 2};
+    uint64_t str[3] = {static_cast<uint64_t>(d.v_ld) * 2, static_cast<uint64_t>(d.v_batch_stride) * 2,
+                       static_cast<uint64_t>(d.v_plane) * 2};
     if (d.batches == 1) str[1] = str[0] * dims[1];
-    uint32_t box[4] = {64, 128, 1, 1};
-    int rc = encode_map_bf16(&p.v_map, d.vt_hi, 4, dims, str, box);
+    uint32_t box[4] = {64, 64, 1, 1};
+    int rc = encode_map_bf16(&p.v_map, d.v_hi, 4, dims, str, box);
     if (rc) return rc;
   }
   p.Lq = d.Lq;

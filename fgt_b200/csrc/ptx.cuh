@@ -170,6 +170,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   d |= static_cast<uint64_t>(2) << 61;                         // layout: SWIZZLE_128B
   return d;
 }
+// Same swizzle, MN-major operand (the N/M index is the contiguous one): a [K rows x 64 elements (128 B)] block per
+// 64-wide slice of the MN extent, 8-row atoms of 1024 B along K; `mn_block_bytes` = distance between the slices.
+// Used for V [keys, d] as the B operand of P.V (K = keys, N = d). Advance K by 8 rows per 1024 B.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t saddr, uint32_t mn_block_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);         // start address  [0,14)
+  d |= static_cast<uint64_t>(mn_block_bytes >> 4) << 16;       // LBO: next 64-element slice along MN
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                 // SBO: next 8 rows along K
+  d |= static_cast<uint64_t>(1) << 46;                         // descriptor version (sm_100)
+  d |= static_cast<uint64_t>(2) << 61;                         // layout: SWIZZLE_128B
+  return d;
+}
+constexpr uint32_t kIdescBMajorMN = 1u << 16;  // instruction-descriptor bit: B operand is MN-major
 // Instruction descriptor: D=f32, A=B=bf16, both K-major, shape M x N (K = 16 per instruction).
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |

@@ -271,9 +271,8 @@ class FGT(nn.Module):
             a = pre + "attention."
             P[name + ".ln_g"] = sd[pre + "norm1.weight"].contiguous().to(dev)
             P[name + ".ln_b"] = sd[pre + "norm1.bias"].contiguous().to(dev)
-            put(name + ".qk", torch.cat([sd[a + "query_embedding.weight"], sd[a + "key_embedding.weight"]], 0),
-                torch.cat([sd[a + "query_embedding.bias"], sd[a + "key_embedding.bias"]], 0))
-            put(name + ".v", sd[a + "value_embedding.weight"], sd[a + "value_embedding.bias"])
+            put(name + ".qkv", torch.cat([sd[a + n + "_embedding.weight"] for n in ("query", "key", "value")], 0),
+                torch.cat([sd[a + n + "_embedding.bias"] for n in ("query", "key", "value")], 0))
             put(name + ".o", sd[a + "output_linear.weight"], sd[a + "output_linear.bias"])
             ffn(pre, name, sd[pre + "norm2.weight"], sd[pre + "norm2.bias"])
 
@@ -429,6 +428,10 @@ class FGT(nn.Module):
 
     def _ffn(self, g, P, name, x, xs, dev):
         """x += FusionFeedForward(LN(x)) (ffn_base.py:53-77, model.py:128-129 / 147-148)."""
+        with lib.scope("ffn"):
+            self._ffn_impl(g, P, name, x, xs, dev)
+
+    def _ffn_impl(self, g, P, name, x, xs, dev):
         rows, d = g.bt * g.n, self.d
         k, s, p = self.ksz[0], self.stride[0], self.padding[0]
         hidden = k * k * self.mlp_c
@@ -478,7 +481,6 @@ class FGT(nn.Module):
         d, zl = self.d, g.zh * g.zw
         T, off = sum(counts), sum(counts[:rank])
         Lzl, Lz = g.Lz, T * zl
-        Lzp = (Lz + 7) // 8 * 8
         plane = g.zones * Lz * d
         key = ("s_all", g.zones, Lz, d)
         if key not in fs["work"]:
@@ -489,13 +491,9 @@ class FGT(nn.Module):
             fs["work"][key] = bufs
         ptrs, s_all = fs["work"][key][fs["layer"] % 2]
         fs["layer"] += 1
-        if name + ".q" not in P:
-            w = P[name + ".qk"]
-            P[name + ".q"] = dict(w, w=w["w"][:, :d].contiguous(), b=w["b"][:d].contiguous(), N=d, name=name + ".q")
-            P[name + ".k"] = dict(w, w=w["w"][:, d:].contiguous(), b=w["b"][d:].contiguous(), N=d, name=name + ".k")
+        self._split_qkv(P, name)
         q = self._buf(g, f"tp_q{T}", (g.zones * Lzl, d), dev, split=True)
-        kk = self._buf(g, f"tp_k{T}", (g.zones * Lz, d), dev, split=True)
-        vt = self._buf(g, f"tp_vt{T}", (g.zones, d, Lzp), dev, split=True, zero=True)
+        kv = self._buf(g, f"tp_kv{T}", (g.zones * Lz, 2 * d), dev, split=True)
         att = self._buf(g, f"tp_att{T}", (g.zones * Lzl, d), dev, split=True)
         lib.rownorm_bcast(x, ptrs, plane, gather=g.zone_map, rows_per_batch=Lzl, total_rows=g.zones * Lzl,
                           dst_batch_rows=Lz, dst_row0=off * zl, eps=LN_EPS, gamma=P[name + ".ln_g"],
@@ -507,15 +505,21 @@ class FGT(nn.Module):
         lib.gemm_tc([lib.ASeg(s_all, d, Lzl, g.zones, 1, sx=d, sy=Lz * d, elem_offset=off * zl * d)], wq["w"], d,
                     out_w=Lzl, out_h=g.zones, box_w=bw, box_h=bh, bn=_pick_bn(d, 1, wq["name"]), bias=wq["b"],
                     out_split=q, os_x=d, os_y=Lzl * d, tag=wq["name"])
-        self._linear([lib.ASeg(s_all, d, g.zones * Lz)], P[name + ".k"], g.zones * Lz, out_split=kk)
-        self._linear([lib.ASeg(s_all, d, g.zones * Lz)], P[name + ".v"], g.zones * Lz, out_split=vt, lin_batch=Lz,
-                     os_z=d * Lzp, os_x=1, os_c=Lzp)
-        lib.attention(q, kk, vt, att, batches=g.zones, heads=self.heads, Lq=Lzl, Lk=Lz, q_ld=d, k_ld=d, vt_ld=Lzp,
-                      out_ld=d, q_batch_stride=Lzl * d, k_batch_stride=Lz * d, vt_batch_stride=d * Lzp,
-                      out_batch_stride=Lzl * d, scale=1.0 / math.sqrt(d // self.heads), tag=name)
+        self._linear([lib.ASeg(s_all, d, g.zones * Lz)], P[name + ".kv"], g.zones * Lz, out_split=kv)
+        lib.attention(q, kv, kv, att, batches=g.zones, heads=self.heads, Lq=Lzl, Lk=Lz, q_ld=d, k_ld=2 * d, v_ld=2 * d,
+                      out_ld=d, q_batch_stride=Lzl * d, k_batch_stride=Lz * 2 * d, v_batch_stride=Lz * 2 * d,
+                      out_batch_stride=Lzl * d, scale=1.0 / math.sqrt(d // self.heads), v_off=d, tag=name)
         self._linear([lib.ASeg(att, d, g.zones * Lzl)], P[name + ".o"], g.zones * Lzl, rowmap=g.zone_map, aux=x,
                      aux_mode=lib.AUX_ADD, out_f32=x)
-        self._ffn(g, P, name, x, xs, dev)
+
+    def _split_qkv(self, P, name):
+        """Q-only and K|V-only slices of the fused temporal projection (frame-sharded TMHSA: Q for the local
+        frames, K|V for the rows of every frame)."""
+        if name + ".q" not in P:
+            d, w = self.d, P[name + ".qkv"]
+            P[name + ".q"] = dict(w, w=w["w"][:, :d].contiguous(), b=w["b"][:d].contiguous(), N=d, name=name + ".q")
+            P[name + ".kv"] = dict(w, w=w["w"][:, d:].contiguous(), b=w["b"][d:].contiguous(), N=2 * d,
+                                   name=name + ".kv")
 
     def _temporal_sharded(self, g, P, name, x, xs, dev):
         """TMHSA over all T frames of the window with this rank holding g.t of them: queries = own frames,
@@ -528,55 +532,58 @@ class FGT(nn.Module):
         d, zl = self.d, g.zh * g.zw
         T, tmax = sum(counts), max(counts)
         Lzl, Lz, Lqp = g.Lz, T * zl, tmax * zl
-        Lzp = (Lz + 7) // 8 * 8
-        if name + ".q" not in P:
-            w = P[name + ".qk"]
-            P[name + ".q"] = dict(w, w=w["w"][:, :d].contiguous(), b=w["b"][:d].contiguous(), N=d, name=name + ".q")
-            P[name + ".k"] = dict(w, w=w["w"][:, d:].contiguous(), b=w["b"][d:].contiguous(), N=d, name=name + ".k")
+        self._split_qkv(P, name)
         s_loc = self._buf(g, f"ts_s{T}", (g.zones * Lqp, d), dev, split=True, zero=True)
         q = self._buf(g, f"ts_q{T}", (g.zones * Lqp, d), dev, split=True)
-        kk = self._buf(g, f"ts_k{T}", (g.zones * Lz, d), dev, split=True)
-        vt = self._buf(g, f"ts_vt{T}", (g.zones, d, Lzp), dev, split=True, zero=True)
+        kv = self._buf(g, f"ts_kv{T}", (g.zones * Lz, 2 * d), dev, split=True)
         att = self._buf(g, f"ts_att{T}", (g.zones * Lzl, d), dev, split=True)
         lib.rownorm(x, None, s_loc, gather=g.zone_map, rows_per_batch=Lzl, total_rows=g.zones * Lzl,
                     dst_batch_rows=Lqp, eps=LN_EPS, gamma=P[name + ".ln_g"], beta=P[name + ".ln_b"])
         s_all = parallel.allgather_zone_rows(s_loc.view(2, g.zones, Lqp, d), counts, zl, fs["group"], fs["work"])
         s_all = s_all.view(2, g.zones * Lz, d)
         self._linear([lib.ASeg(s_loc, d, g.zones * Lqp)], P[name + ".q"], g.zones * Lqp, out_split=q)
-        self._linear([lib.ASeg(s_all, d, g.zones * Lz)], P[name + ".k"], g.zones * Lz, out_split=kk)
-        self._linear([lib.ASeg(s_all, d, g.zones * Lz)], P[name + ".v"], g.zones * Lz, out_split=vt, lin_batch=Lz,
-                     os_z=d * Lzp, os_x=1, os_c=Lzp)
-        lib.attention(q, kk, vt, att, batches=g.zones, heads=self.heads, Lq=Lzl, Lk=Lz, q_ld=d, k_ld=d, vt_ld=Lzp,
-                      out_ld=d, q_batch_stride=Lqp * d, k_batch_stride=Lz * d, vt_batch_stride=d * Lzp,
-                      out_batch_stride=Lzl * d, scale=1.0 / math.sqrt(d // self.heads), tag=name)
+        self._linear([lib.ASeg(s_all, d, g.zones * Lz)], P[name + ".kv"], g.zones * Lz, out_split=kv)
+        lib.attention(q, kv, kv, att, batches=g.zones, heads=self.heads, Lq=Lzl, Lk=Lz, q_ld=d, k_ld=2 * d, v_ld=2 * d,
+                      out_ld=d, q_batch_stride=Lqp * d, k_batch_stride=Lz * 2 * d, v_batch_stride=Lz * 2 * d,
+                      out_batch_stride=Lzl * d, scale=1.0 / math.sqrt(d // self.heads), v_off=d, tag=name)
         self._linear([lib.ASeg(att, d, g.zones * Lzl)], P[name + ".o"], g.zones * Lzl, rowmap=g.zone_map, aux=x,
                      aux_mode=lib.AUX_ADD, out_f32=x)
-        self._ffn(g, P, name, x, xs, dev)
 
     def _temporal(self, g, P, name, x, xs, dev):
         """TemporalTransformer.forward (model.py:124-130) with TMHSA (attention_base.py:76-106)."""
-        if getattr(self, "_fshard", None) is not None:
-            return self._temporal_sharded(g, P, name, x, xs, dev)
+        with lib.scope("tmhsa"):
+            if getattr(self, "_fshard", None) is not None:
+                self._temporal_sharded(g, P, name, x, xs, dev)
+            else:
+                self._tmhsa(g, P, name, x, dev)
+        self._ffn(g, P, name, x, xs, dev)
+
+    def _tmhsa(self, g, P, name, x, dev):
+        """x += TMHSA(LN(x)): LayerNorm + zone gather, fused QKV GEMM, dense flash attention, out-projection."""
         d, rows_z = self.d, g.zones * g.Lz
         s_zm = self._buf(g, "t_s", (rows_z, d), dev, split=True)
-        qk = self._buf(g, "t_qk", (rows_z, 2 * d), dev, split=True)
-        vt = self._buf(g, "t_vt", (g.zones, d, g.Lzp), dev, split=True, zero=True)
+        qkv = self._buf(g, "t_qkv", (rows_z, 3 * d), dev, split=True)
         att = self._buf(g, "t_att", (rows_z, d), dev, split=True)
         lib.rownorm(x, None, s_zm, gather=g.zone_map, rows_per_batch=rows_z, total_rows=rows_z,
                     dst_batch_rows=rows_z, eps=LN_EPS, gamma=P[name + ".ln_g"], beta=P[name + ".ln_b"])
         a = [lib.ASeg(s_zm, d, rows_z)]
-        self._linear(a, P[name + ".qk"], rows_z, out_split=qk)
-        self._linear(a, P[name + ".v"], rows_z, out_split=vt, lin_batch=g.Lz, os_z=d * g.Lzp, os_x=1, os_c=g.Lzp)
-        lib.attention(qk, qk, vt, att, batches=g.zones, heads=self.heads, Lq=g.Lz, Lk=g.Lz, q_ld=2 * d, k_ld=2 * d,
-                      vt_ld=g.Lzp, out_ld=d, q_batch_stride=g.Lz * 2 * d, k_batch_stride=g.Lz * 2 * d,
-                      vt_batch_stride=d * g.Lzp, out_batch_stride=g.Lz * d, scale=1.0 / math.sqrt(d // self.heads),
-                      k_off=d, tag=name)
+        self._linear(a, P[name + ".qkv"], rows_z, out_split=qkv)  # one N=1536 GEMM: Q | K | V, all row-major
+        lib.attention(qkv, qkv, qkv, att, batches=g.zones, heads=self.heads, Lq=g.Lz, Lk=g.Lz, q_ld=3 * d, k_ld=3 * d,
+                      v_ld=3 * d, out_ld=d, q_batch_stride=g.Lz * 3 * d, k_batch_stride=g.Lz * 3 * d,
+                      v_batch_stride=g.Lz * 3 * d, out_batch_stride=g.Lz * d, scale=1.0 / math.sqrt(d // self.heads),
+                      k_off=d, v_off=2 * d, tag=name)
         self._linear([lib.ASeg(att, d, rows_z)], P[name + ".o"], rows_z, rowmap=g.zone_map, aux=x,
                      aux_mode=lib.AUX_ADD, out_f32=x)
-        self._ffn(g, P, name, x, xs, dev)
 
     def _spatial(self, g, P, name, x, xs, f, fs, dev):
         """SpatialTransformer.forward (model.py:144-149) with SWMHSA (attention_flow.py:115-171)."""
+        with lib.scope("swmhsa"):
+            self._swmhsa(g, P, name, x, xs, f, fs, dev)
+        self._ffn(g, P, name, x, xs, dev)
+
+    def _swmhsa(self, g, P, name, x, xs, f, fs, dev):
+        """x += SWMHSA(x, f): flow gate, pooled global tokens, LayerNorms, Q|K and V GEMMs, windowed flash attention,
+        out-projection."""
         d, df, bt = self.d, self.df, g.bt
         rows = bt * g.n
         fp = self._buf(g, "s_fp", (rows, df), dev)
@@ -584,8 +591,7 @@ class FGT(nn.Module):
         vg = self._buf(g, "s_vg", (bt * g.G, d), dev)
         qkn = self._buf(g, "s_qkn", (bt * g.R, d + df), dev, split=True, zero=True)
         vn = self._buf(g, "s_vn", (bt * g.R, d), dev, split=True, zero=True)
-        qk = self._buf(g, "s_qk", (bt * g.R, 2 * d), dev, split=True)
-        vt = self._buf(g, "s_vt", (bt, d, g.R), dev, split=True)
+        qkv = self._buf(g, "s_qkv", (bt * g.R, 3 * d), dev, split=True)
         att = self._buf(g, "s_att", (bt * g.nwp * 64, d), dev, split=True)
         # flow re-weighting gate: f' = f * sigmoid(W_r [x; f] + b_r)   (attention_flow.py:126-128)
         self._linear([lib.ASeg(xs, d, rows), lib.ASeg(fs, df, rows)], P[name + ".gate"], rows, act=lib.ACT_SIGMOID,
@@ -603,16 +609,16 @@ class FGT(nn.Module):
                     eps=LN_EPS)
         lib.rownorm(vg, None, vn, rows_per_batch=g.G, total_rows=bt * g.G, dst_batch_rows=g.R, dst_row0=nl,
                     eps=LN_EPS)
-        self._linear([lib.ASeg(qkn, d + df, bt * g.R)], P[name + ".qk"], bt * g.R, out_split=qk)
-        self._linear([lib.ASeg(vn, d, bt * g.R)], P[name + ".v"], bt * g.R, out_split=vt, lin_batch=g.R,
-                     os_z=d * g.R, os_x=1, os_c=g.R)
-        lib.attention(qk, qk, vt, att, batches=bt, heads=self.heads, Lq=nl, Lk=g.R, Lk_rows=g.R, q_ld=2 * d,
-                      k_ld=2 * d, vt_ld=g.R, out_ld=d, q_batch_stride=g.R * 2 * d, k_batch_stride=g.R * 2 * d,
-                      vt_batch_stride=d * g.R, out_batch_stride=nl * d, scale=1.0 / math.sqrt(d // self.heads),
-                      mode=1, glob_start=nl, glob_count=g.G, k_off=d, tag=name)
+        # Q | K from the 768-wide normalised rows, V from the 512-wide ones: two GEMMs into one [rows, 3d] buffer
+        self._linear([lib.ASeg(qkn, d + df, bt * g.R)], P[name + ".qk"], bt * g.R, out_split=qkv, os_x=3 * d)
+        self._linear([lib.ASeg(vn, d, bt * g.R)], P[name + ".v"], bt * g.R, out_split=qkv, os_x=3 * d,
+                     out_elem_offset=2 * d)
+        lib.attention(qkv, qkv, qkv, att, batches=bt, heads=self.heads, Lq=nl, Lk=g.R, Lk_rows=g.R, q_ld=3 * d,
+                      k_ld=3 * d, v_ld=3 * d, out_ld=d, q_batch_stride=g.R * 3 * d, k_batch_stride=g.R * 3 * d,
+                      v_batch_stride=g.R * 3 * d, out_batch_stride=nl * d, scale=1.0 / math.sqrt(d // self.heads),
+                      mode=1, glob_start=nl, glob_count=g.G, k_off=d, v_off=2 * d, tag=name)
         self._linear([lib.ASeg(att, d, bt * nl)], P[name + ".o"], bt * nl, rowmap=g.win_map, aux=x,
                      aux_mode=lib.AUX_ADD, out_f32=x)
-        self._ffn(g, P, name, x, xs, dev)
 
     # ------------------------------------------------------------------ forward
     def enable_cuda_graph(self, on=True):
@@ -650,6 +656,7 @@ class FGT(nn.Module):
         H2, W2, OH, OW = H // 2, W // 2, g.OH, g.OW
 
         # ---- frame encoder (model.py:53-66)
+        lib._scope[1:] = ["encoder"]  # module labels for the per-launch profiler (bench.py "modules")
         incol = B("in_col", (bt, H2, W2, 64), split=True)
         lib.im2col_nchw(frames, mk, incol, k=3, stride=2, pad=1, replicate=False, OH=H2, OW=W2, tag="enc0")
         e0 = B("e0", (bt, H2, W2, 64), split=True)
@@ -676,6 +683,7 @@ class FGT(nn.Module):
         self._conv(x0, 256, bt, OH, OW, P["enc16"], 3, out_split=enc, out_f32=enc_f, extra_seg=(e14, 256), groups=1,
                    seg_counts=[256, 256])
         # ---- flow encoder (model.py:206-212)
+        lib._scope[-1] = "flow_encoder"
         fcol = B("f_col", (bt, H, W, 64), split=True)
         lib.im2col_nchw(fl, None, fcol, k=5, stride=1, pad=2, replicate=True, OH=H, OW=W, tag="fenc1")
         f1 = B("f1", (bt, H, W, 64), split=True)
@@ -687,6 +695,7 @@ class FGT(nn.Module):
         self._conv(f2, 128, bt, H2, W2, P["fenc3"], 3, out_split=f3)
         self._conv(f3, 128, bt, H2, W2, P["fenc4"], 3, stride=2, out_split=f4)
         # ---- patch embedding (model.py:261-262,270-271): conv output NHWC == token-major
+        lib._scope[-1] = "patch_embed"
         rows = bt * g.n
         xa = B("x_a", (rows, self.d))
         xb = B("x_b", (rows, self.d))
@@ -701,6 +710,7 @@ class FGT(nn.Module):
         self._cap("tok0", xa)
         self._cap("ftok", f)
         # ---- transformer (model.py:272-277)
+        lib._scope[-1] = "pos_emb"
         self._temporal(g, P, "t0", xa, xs, dev)
         self._cap("t0", xa)
         lib.dwconv3x3_res(xa, bt, g.h, g.w, self.d, P["pos_w"], P["pos_b"], xb, xs)
@@ -712,11 +722,13 @@ class FGT(nn.Module):
             self._spatial(g, P, f"s{i + 1}", x, xs, f, fs, dev)
         self._cap("tok_final", x)
         # ---- vec2patch + skip (model.py:278-279)
+        lib._scope[-1] = "vec2patch"
         v2p = B("v2p", (rows, k * k * self.cnum * 2))
         feat = B("feat", (bt, OH, OW, self.cnum * 2), split=True)
         self._linear([lib.ASeg(xs, self.d, rows)], P["vec2patch"], rows, out_f32=v2p)
         lib.fold(v2p, bt, g.h, g.w, self.cnum * 2, k, k, s, p, OH, OW, normalize=False, add=enc_f, out_split=feat)
         # ---- decoder (model.py:188-193,281-282)
+        lib._scope[-1] = "decoder"
         c2 = self.cnum * 2
         d1 = B("d1", (bt, H2, W2, c2), split=True)
         d2 = B("d2", (bt, H2, W2, c2 // 2), split=True)
@@ -728,6 +740,7 @@ class FGT(nn.Module):
         y4 = B("dec4_y", (32, bt * H * W))  # column-planar partial products
         self._linear([lib.ASeg(d3, c2 // 2, bt * H * W)], P["dec4t"], bt * H * W, out_f32=y4, os_x=1, os_c=bt * H * W)
         lib.tapsum(y4, bt, H, W, 3, 3, P["dec4"]["b"], lib.ACT_TANH, out, nchw=True, tag="dec4")
+        lib._scope[1:] = []
         return out
 
 

@@ -44,7 +44,7 @@ class FgtGemmDesc(ctypes.Structure):
 class FgtAttnDesc(ctypes.Structure):
     _fields_ = [("q_hi", _c_p), ("q_plane", _c_ll), ("q_batch_stride", _c_ll), ("q_ld", ctypes.c_int),
                 ("k_hi", _c_p), ("k_plane", _c_ll), ("k_batch_stride", _c_ll), ("k_ld", ctypes.c_int),
-                ("vt_hi", _c_p), ("vt_plane", _c_ll), ("vt_batch_stride", _c_ll), ("vt_ld", ctypes.c_int),
+                ("v_hi", _c_p), ("v_plane", _c_ll), ("v_batch_stride", _c_ll), ("v_ld", ctypes.c_int),
                 ("out_hi", _c_p), ("out_plane", _c_ll), ("out_batch_stride", _c_ll), ("out_ld", ctypes.c_int),
                 ("batches", ctypes.c_int), ("heads", ctypes.c_int), ("head_dim", ctypes.c_int),
                 ("Lq", ctypes.c_int), ("Lk", ctypes.c_int), ("Lk_rows", ctypes.c_int),
@@ -162,6 +162,21 @@ def check_rc(rc, what):
 # Kernel-launch counter (bench.py's "gpu_launches") and optional per-launch CUDA-event profiler.
 COUNTERS = {"launches": 0}
 _profile = None  # list of (kernel, tag, flops, bytes, ev_start, ev_end) when enabled
+_scope = [""]    # module label of the launches being issued (bench.py's per-module roofline block)
+
+
+class scope:
+    """`with lib.scope("tmhsa"):` labels every launch recorded by the profiler inside the block."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        _scope.append(self.name)
+
+    def __exit__(self, *exc):
+        _scope.pop()
+        return False
 
 
 def profile_start():
@@ -170,11 +185,11 @@ def profile_start():
 
 
 def profile_stop():
-    """Returns [(kernel, tag, algorithmic_flops, algorithmic_bytes, milliseconds)]; syncs the device."""
+    """Returns [(kernel, tag, algorithmic_flops, algorithmic_bytes, milliseconds, module_scope)]; syncs the device."""
     global _profile
     recs, _profile = _profile, None
     torch.cuda.synchronize()
-    return [(k, t, fl, by, e0.elapsed_time(e1)) for (k, t, fl, by, e0, e1) in recs]
+    return [(k, t, fl, by, e0.elapsed_time(e1), sc) for (k, t, fl, by, sc, e0, e1) in recs]
 
 
 class _Prof:
@@ -193,7 +208,7 @@ class _Prof:
         if _profile is not None and exc[0] is None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            _profile.append(self.meta + (self.e0, e1))
+            _profile.append(self.meta + (_scope[-1], self.e0, e1))
         return False
 
 
@@ -295,16 +310,16 @@ def gemm_tc(segs, w_split, N, *, kx=1, ky=1, kz=1, stride=1, dil=1, pad_x=0, pad
         check(lib.fgt_gemm_tc(ctypes.byref(d), stream_ptr()), "fgt_gemm_tc")
 
 
-def attention(q, k, vt, out, *, batches, heads, Lq, Lk, Lk_rows=None, q_ld, k_ld, vt_ld, out_ld,
-              q_batch_stride, k_batch_stride, vt_batch_stride, out_batch_stride, scale, mode=0,
-              glob_start=0, glob_count=0, q_off=0, k_off=0, tag=""):
-    """fgt_attention launcher. q/k/vt/out are split-bf16 tensors; strides in elements; q_off/k_off are
-    element offsets into the plane (e.g. when Q and K share one [rows, 2*C] buffer)."""
+def attention(q, k, v, out, *, batches, heads, Lq, Lk, Lk_rows=None, q_ld, k_ld, v_ld, out_ld,
+              q_batch_stride, k_batch_stride, v_batch_stride, out_batch_stride, scale, mode=0,
+              glob_start=0, glob_count=0, q_off=0, k_off=0, v_off=0, tag=""):
+    """fgt_attention launcher. q/k/v/out are split-bf16 row-major tensors; strides in elements; q_off/k_off/v_off
+    are element offsets into the plane (e.g. when Q, K and V share one [rows, 3*C] projection buffer)."""
     lib = load()
     d = FgtAttnDesc()
     d.q_hi, d.q_plane, d.q_batch_stride, d.q_ld = q.data_ptr() + 2 * q_off, plane_elems(q), q_batch_stride, q_ld
     d.k_hi, d.k_plane, d.k_batch_stride, d.k_ld = k.data_ptr() + 2 * k_off, plane_elems(k), k_batch_stride, k_ld
-    d.vt_hi, d.vt_plane, d.vt_batch_stride, d.vt_ld = vt.data_ptr(), plane_elems(vt), vt_batch_stride, vt_ld
+    d.v_hi, d.v_plane, d.v_batch_stride, d.v_ld = v.data_ptr() + 2 * v_off, plane_elems(v), v_batch_stride, v_ld
     d.out_hi, d.out_plane, d.out_batch_stride, d.out_ld = out.data_ptr(), plane_elems(out), out_batch_stride, out_ld
     d.batches, d.heads, d.head_dim = batches, heads, 128
     d.Lq, d.Lk = Lq, Lk

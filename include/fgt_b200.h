@@ -112,9 +112,9 @@ int fgt_gemm_tc(const FgtGemmDesc* desc, fgt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * fgt_attention: fused softmax(Q K^T * scale) V (flash-style, scores never leave the SM).
- * Q, K: split-bf16 row-major [batch, rows, heads*128]; V is supplied TRANSPOSED,
- * V^T: split-bf16 [batch, heads*128, vt_ld] (keys contiguous) — the V projection GEMM writes it
- * that way directly (os_c = vt_ld, os_x = 1). Output: split-bf16 [batch, Lq, heads*128].
+ * Q, K, V: split-bf16 row-major [batch, rows, heads*128] with their own leading dimensions, so one
+ * fused QKV projection buffer [rows, 3*heads*128] can feed all three (V is consumed as an MN-major
+ * tcgen05 B operand; no transposed copy). Output: split-bf16 [batch, Lq, heads*128].
  *   mode 0 (dense)   : every query row attends to keys [0, Lk)            (TMHSA zones)
  *   mode 1 (windowed): query tile i (=two 64-token windows) attends to its own two 64-key tiles
  *                      (block-diagonal) plus the shared keys [glob_start, glob_start+glob_count)
@@ -123,7 +123,7 @@ int fgt_gemm_tc(const FgtGemmDesc* desc, fgt_stream_t stream);
 typedef struct {
   const void* q_hi; long long q_plane; long long q_batch_stride; int q_ld;
   const void* k_hi; long long k_plane; long long k_batch_stride; int k_ld;
-  const void* vt_hi; long long vt_plane; long long vt_batch_stride; int vt_ld;
+  const void* v_hi; long long v_plane; long long v_batch_stride; int v_ld;
   void* out_hi; long long out_plane; long long out_batch_stride; int out_ld;
   int batches, heads, head_dim; /* head_dim must be 128 */
   int Lq;                       /* query rows per batch */

@@ -2,7 +2,8 @@
 product path; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 legs may use it).
 
-A functional, state_dict-driven restatement in plain PyTorch (CPU, fp32 or fp64) of
+A functional, state_dict-driven restatement in plain PyTorch (fp32 or fp64; device-agnostic, so bench.py's
+GPU-eager baseline leg can run the same code on CUDA tensors through cuBLAS/cuDNN) of
 /root/reference/FGT/models/model.py and FGT/models/transformer_base/*.py. Every function cites the
 reference lines it restates. Pinned against the imported reference itself by
 tests/golden/make_golden.py (run in the build container, where /root/reference exists); the
@@ -73,7 +74,7 @@ def tmhsa(x, sd, pre, t, h, w, group=2, heads=4):
     q = F.linear(g, sd[pre + "query_embedding.weight"], sd[pre + "query_embedding.bias"])
     k = F.linear(g, sd[pre + "key_embedding.weight"], sd[pre + "key_embedding.bias"])
     v = F.linear(g, sd[pre + "value_embedding.weight"], sd[pre + "value_embedding.bias"])
-    out = torch.empty(b, t, H, W, c, dtype=x.dtype)
+    out = torch.empty(b, t, H, W, c, dtype=x.dtype, device=x.device)
 
     def zone(z, iy, ix):
         z = z.reshape(b, t, H, W, heads, d)[:, :, iy * zh:(iy + 1) * zh, ix * zw:(ix + 1) * zw]
@@ -143,7 +144,7 @@ def fusion_ffn(x, sd, pre, n_vecs, out_hw, kernel=(7, 7), stride=(3, 3), padding
     kk = kernel[0] * kernel[1]
     cols = y.reshape(-1, n_vecs, c).transpose(1, 2)
     img = F.fold(cols, out_hw, kernel, stride=stride, padding=padding)
-    cnt = F.fold(torch.ones(cols.shape[0], kk, n_vecs, dtype=y.dtype), out_hw, kernel, stride=stride, padding=padding)
+    cnt = F.fold(torch.ones(cols.shape[0], kk, n_vecs, dtype=y.dtype, device=y.device), out_hw, kernel, stride=stride, padding=padding)
     y = F.unfold(img / cnt, kernel, stride=stride, padding=padding).transpose(1, 2).reshape(b, n, c)
     return F.linear(F.relu(y), sd[pre + "conv2.2.weight"], sd[pre + "conv2.2.bias"])
 

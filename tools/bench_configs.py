@@ -43,7 +43,7 @@ for name, (t, H, W) in {"c2_432x240_T10": (10, 240, 432), "c4_432x240_T18": (18,
         model(*clip)
         recs = lib.profile_stop()
     agg = {}
-    for kern, tag, fl, by, m in recs:
+    for kern, tag, fl, by, m, _sc in recs:
         key = kern if kern != "flash" else ("flash_temporal" if tag.startswith("t") else "flash_spatial")
         a = agg.setdefault(key, [0.0, 0.0, 0.0])
         a[0] += m

@@ -41,7 +41,7 @@ def breakdown(fn, reps=3):
         fn()
     recs = lib.profile_stop()
     agg = {}
-    for k, tag, fl, by, ms in recs:
+    for k, tag, fl, by, ms, _sc in recs:
         a = agg.setdefault(k, dict(ms=0.0, flops=0.0, bytes=0.0, n=0))
         a["ms"] += ms / reps
         a["flops"] += fl / reps

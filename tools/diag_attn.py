@@ -16,18 +16,15 @@ torch.manual_seed(0)
 
 def dense_case(batches, heads, L, qscale=1.0):
     C = heads * 128
-    Lp = (L + 7) // 8 * 8
     q = torch.randn(batches, L, C, device=dev) * qscale
     k = torch.randn(batches, L, C, device=dev)
     v = torch.randn(batches, L, C, device=dev)
     qs, ks = lib.to_split(q), lib.to_split(k)
-    vt = torch.zeros(batches, C, Lp, device=dev)
-    vt[:, :, :L] = v.transpose(1, 2)
-    vts = lib.to_split(vt)
+    vs = lib.to_split(v)
     out = lib.empty_split((batches, L, C), dev)
     out.fill_(float("nan"))
-    lib.attention(qs, ks, vts, out, batches=batches, heads=heads, Lq=L, Lk=L, q_ld=C, k_ld=C, vt_ld=Lp, out_ld=C,
-                  q_batch_stride=L * C, k_batch_stride=L * C, vt_batch_stride=C * Lp, out_batch_stride=L * C,
+    lib.attention(qs, ks, vs, out, batches=batches, heads=heads, Lq=L, Lk=L, q_ld=C, k_ld=C, v_ld=C, out_ld=C,
+                  q_batch_stride=L * C, k_batch_stride=L * C, v_batch_stride=L * C, out_batch_stride=L * C,
                   scale=1 / math.sqrt(128))
     torch.cuda.synchronize()
     qh = q.double().reshape(batches, L, heads, 128).transpose(1, 2)
@@ -47,12 +44,12 @@ def window_case(frames, heads, nwin, nglob, qscale=1.0):
     k = torch.randn(frames, rows, C, device=dev)
     v = torch.randn(frames, rows, C, device=dev)
     qs, ks = lib.to_split(q), lib.to_split(k)
-    vts = lib.to_split(v.transpose(1, 2).contiguous())
+    vs = lib.to_split(v)
     out = lib.empty_split((frames, nwp * 64, C), dev)
     out.fill_(float("nan"))
-    lib.attention(qs, ks, vts, out, batches=frames, heads=heads, Lq=nwp * 64, Lk=rows, Lk_rows=rows, q_ld=C, k_ld=C,
-                  vt_ld=rows, out_ld=C, q_batch_stride=nwp * 64 * C, k_batch_stride=rows * C,
-                  vt_batch_stride=C * rows, out_batch_stride=nwp * 64 * C, scale=1 / math.sqrt(128), mode=1,
+    lib.attention(qs, ks, vs, out, batches=frames, heads=heads, Lq=nwp * 64, Lk=rows, Lk_rows=rows, q_ld=C, k_ld=C,
+                  v_ld=C, out_ld=C, q_batch_stride=nwp * 64 * C, k_batch_stride=rows * C,
+                  v_batch_stride=rows * C, out_batch_stride=nwp * 64 * C, scale=1 / math.sqrt(128), mode=1,
                   glob_start=nwp * 64, glob_count=nglob)
     torch.cuda.synchronize()
     ref = torch.empty(frames, nwp * 64, C, dtype=torch.double, device=dev)

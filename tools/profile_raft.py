@@ -21,7 +21,7 @@ with torch.no_grad():
     m(a, b, iters=20, test_mode=True)
     recs = lib.profile_stop()
 agg = collections.OrderedDict()
-for k, tag, fl, by, ms in recs:
+for k, tag, fl, by, ms, _sc in recs:
     key = f"{k}:{tag}"
     e = agg.setdefault(key, [0, 0.0, 0.0])
     e[0] += 1

@@ -11,10 +11,9 @@ from fgt_b200 import lib  # noqa: E402
 
 dev = torch.device("cuda:0")
 L, C, heads, batches = 1800, 512, 4, 4
-Lp = L
 q = lib.to_split(torch.randn(batches, L, C, device=dev) * 3)
 k = lib.to_split(torch.randn(batches, L, C, device=dev))
-vt = lib.to_split(torch.randn(batches, C, Lp, device=dev))
+v = lib.to_split(torch.randn(batches, L, C, device=dev))
 out = lib.empty_split((batches, L, C), dev)
 trace = torch.zeros(3 * 64 * 8, dtype=torch.int64, device=dev)
 L_ = lib.load()
@@ -22,8 +21,8 @@ L_.fgt_debug_flash_trace.argtypes = [ctypes.c_void_p]
 
 
 def run():
-    lib.attention(q, k, vt, out, batches=batches, heads=heads, Lq=L, Lk=L, q_ld=C, k_ld=C, vt_ld=Lp, out_ld=C,
-                  q_batch_stride=L * C, k_batch_stride=L * C, vt_batch_stride=C * Lp, out_batch_stride=L * C,
+    lib.attention(q, k, v, out, batches=batches, heads=heads, Lq=L, Lk=L, q_ld=C, k_ld=C, v_ld=C, out_ld=C,
+                  q_batch_stride=L * C, k_batch_stride=L * C, v_batch_stride=L * C, out_batch_stride=L * C,
                   scale=1 / math.sqrt(128))
 
 
