@@ -40,8 +40,8 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int encode_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes, const uint32_t* box) {
+static int encode_map_any(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_err(FGT_ERR_DEVICE, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   cuuint64_t gdim[5];
@@ -61,7 +61,7 @@ int encode_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t
                      (unsigned long long)gstr[i]);
   }
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return set_err(FGT_ERR_ARG, "tensor map: base misaligned");
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+  CUresult r = fn(out, dtype, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
                   gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
@@ -72,6 +72,16 @@ int encode_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t
                    (unsigned long long)(rank > 4 ? gdim[4] : 0), bx[0], rank > 1 ? bx[1] : 0, rank > 2 ? bx[2] : 0,
                    rank > 3 ? bx[3] : 0, rank > 4 ? bx[4] : 0);
   return FGT_OK;
+}
+
+int encode_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box) {
+  return encode_map_any(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box);
+}
+
+int encode_map_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box) {
+  return encode_map_any(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box);
 }
 
 bool pdl_enabled() {

@@ -31,6 +31,9 @@ int set_err(int code, const char* fmt, ...);
 // dims[0] is the contiguous dimension; strides_bytes has rank-1 entries (dims 1..rank-1).
 int encode_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box);
+// Same for fp32 elements (epilogue TMA stores of fp32 outputs).
+int encode_map_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box);
 
 int num_sms();
 

@@ -107,12 +107,17 @@ __global__ void im2col_nchw_kernel(const float* __restrict__ s0, int c0, const f
       }
       v[j] = val;
     }
-    uint32_t hw[4], lw[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) split_bf16x2(v[2 * t], v[2 * t + 1], hw[t], lw[t]);
     const long long o = ((static_cast<long long>(b) * OH + oy) * OW + ox) * cpad + g * 8;
-    *reinterpret_cast<uint4*>(hi + o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-    *reinterpret_cast<uint4*>(hi + plane + o) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    if (plane == 0) {  // single-plane fp16 rows (input of a 1-term layer)
+      *reinterpret_cast<uint4*>(hi + o) = make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]),
+                                                     pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
+    } else {
+      uint32_t hw[4], lw[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) split_bf16x2(v[2 * t], v[2 * t + 1], hw[t], lw[t]);
+      *reinterpret_cast<uint4*>(hi + o) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      *reinterpret_cast<uint4*>(hi + plane + o) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
   }
 }
 

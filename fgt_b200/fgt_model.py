@@ -137,6 +137,13 @@ def _pick_box(ow, oh):
     return best[1], best[2]
 
 
+# MMA terms of the flow branch (flow encoder + f_patch2vec). 1 = single-plane fp16 operands and activations (one MMA per
+# K step instead of three, half the activation bytes): the flow features only steer the spatial attention's gate and
+# Q/K, the flow tokens themselves stay within 1e-3 of the fp32 reference (fp16 has three more mantissa bits than bf16)
+# and the end-to-end error of the whole branch in fp16 is < 1e-4 (tools/precision_study.py). Every other
+# layer class needs the 3-term split product: each costs 2e-4..7e-4 end to end on its own even in fp16.
+_FLOW_TERMS = int(os.environ.get("FGT_FLOW_TERMS", "1"))
+
 # Layers whose output-channel tile is 256 instead of 128 (measured: only the 640->512 grouped encoder
 # conv gains, 0.443 -> 0.403 ms; smaller problems lose to wave quantisation). Tuning knob for experiments.
 _BN256 = os.environ.get("FGT_BN256", "enc10").split(",")
@@ -245,17 +252,19 @@ class FGT(nn.Module):
         for i in (2, 4, 6, 8):
             conv(f"enc{i}", enc + str(i))
         # tiny-channel first layers consume im2col rows (fgt_im2col_nchw): one K=64 GEMM each
-        for name, key in (("enc0", enc + "0"), ("fenc1", "flow_encoder.1.featureConv")):
-            P[name] = dict(w=pack_weight_im2col(sd[key + ".weight"]).to(dev), b=sd[key + ".bias"].contiguous().to(dev),
-                           N=sd[key + ".weight"].shape[0], name=name)
+        fh = _FLOW_TERMS == 1
+        for name, key, half in (("enc0", enc + "0", False), ("fenc1", "flow_encoder.1.featureConv", fh)):
+            P[name] = dict(w=pack_weight_im2col(sd[key + ".weight"], half=half).to(dev),
+                           b=sd[key + ".bias"].contiguous().to(dev), N=sd[key + ".weight"].shape[0], name=name)
         conv("enc10", enc + "10", [128, 192])
         conv("enc12", enc + "12", [64, 128])
         conv("enc14", enc + "14", [32, 48])
         conv("enc16", enc + "16", [256, 256])
-        for i in (2, 3, 4):
-            conv(f"fenc{i}", f"flow_encoder.{i}.featureConv")
+        for name, key in (("fenc2", "flow_encoder.2.featureConv"), ("fenc3", "flow_encoder.3.featureConv"),
+                          ("fenc4", "flow_encoder.4.featureConv"), ("f_patch2vec", "f_patch2vec")):
+            P[name] = dict(w=pack_weight(sd[key + ".weight"], half=fh).to(dev), b=sd[key + ".bias"].contiguous().to(dev),
+                           N=sd[key + ".weight"].shape[0], name=name)
         conv("patch2vec", "patch2vec")
-        conv("f_patch2vec", "f_patch2vec")
         P["pos_w"] = sd["add_pos_emb.proj.weight"].reshape(-1).contiguous().to(dev)
         P["pos_b"] = sd["add_pos_emb.proj.bias"].contiguous().to(dev)
         perm_ffn = self._perm_hidden(self.mlp_c).to(sd["patch2vec.weight"].device)
@@ -288,9 +297,10 @@ class FGT(nn.Module):
             put(name + ".qk", torch.cat([wq, wk], 0), torch.cat([bq, bk], 0))
             put(name + ".v", wv, bv)
             put(name + ".o", sd[a + "output_linear.weight"], sd[a + "output_linear.bias"])
-            P[name + ".gk_w"] = sd[a + "global_extract_k.weight"].reshape(-1).contiguous().to(dev)
+            # depthwise pooling weights tap-major [gd*gd, C] (fgt_swin_prep reads one coalesced row per tap)
+            P[name + ".gk_w"] = sd[a + "global_extract_k.weight"].reshape(self.d + self.df, -1).t().contiguous().to(dev)
             P[name + ".gk_b"] = sd[a + "global_extract_k.bias"].contiguous().to(dev)
-            P[name + ".gv_w"] = sd[a + "global_extract_v.weight"].reshape(-1).contiguous().to(dev)
+            P[name + ".gv_w"] = sd[a + "global_extract_v.weight"].reshape(self.d, -1).t().contiguous().to(dev)
             P[name + ".gv_b"] = sd[a + "global_extract_v.bias"].contiguous().to(dev)
             ffn(pre, name, sd[pre + "norm.weight"], sd[pre + "norm.bias"])
 
@@ -386,7 +396,7 @@ class FGT(nn.Module):
     # ------------------------------------------------------------------ op helpers
     @staticmethod
     def _conv(x, cin, n, h, w, wp, k, *, stride=1, pad=None, act=lib.ACT_LEAKY02, out_split=None, out_f32=None,
-              extra_seg=None, groups=1, seg_counts=None, nchw_out=False):
+              extra_seg=None, groups=1, seg_counts=None, nchw_out=False, terms=3, out_f16=None):
         """NHWC split x [2,n,h,w,cin] (+ optional second segment) -> conv -> NHWC outputs."""
         pad = k // 2 if pad is None else pad
         oh = (h + 2 * pad - k) // stride + 1
@@ -406,7 +416,7 @@ class FGT(nn.Module):
             strides = dict(os_z=oh * ow * N, os_y=ow * N, os_x=N, os_c=1)
         lib.gemm_tc(segs, wp["w"], N, kx=k, ky=k, stride=stride, pad_x=pad, pad_y=pad, groups=groups, out_w=ow,
                     out_h=oh, out_z=n, box_w=bw, box_h=bh, bn=_pick_bn(N // groups, groups, wp["name"]), bias=wp["b"], act=act,
-                    out_f32=out_f32, out_split=out_split, tag=wp["name"], **strides)
+                    out_f32=out_f32, out_split=out_split, out_f16=out_f16, tag=wp["name"], terms=terms, **strides)
         return oh, ow
 
     @staticmethod
@@ -587,8 +597,6 @@ class FGT(nn.Module):
         d, df, bt = self.d, self.df, g.bt
         rows = bt * g.n
         fp = self._buf(g, "s_fp", (rows, df), dev)
-        kg = self._buf(g, "s_kg", (bt * g.G, d + df), dev)
-        vg = self._buf(g, "s_vg", (bt * g.G, d), dev)
         qkn = self._buf(g, "s_qkn", (bt * g.R, d + df), dev, split=True, zero=True)
         vn = self._buf(g, "s_vn", (bt * g.R, d), dev, split=True, zero=True)
         qkv = self._buf(g, "s_qkv", (bt * g.R, 3 * d), dev, split=True)
@@ -596,19 +604,11 @@ class FGT(nn.Module):
         # flow re-weighting gate: f' = f * sigmoid(W_r [x; f] + b_r)   (attention_flow.py:126-128)
         self._linear([lib.ASeg(xs, d, rows), lib.ASeg(fs, df, rows)], P[name + ".gate"], rows, act=lib.ACT_SIGMOID,
                      aux=f, aux_mode=lib.AUX_MUL, out_f32=fp)
-        # pooled global tokens (attention_flow.py:135,145)
-        lib.dwpool(x, fp, bt, g.h, g.w, self.gd, g.gh, g.gw, P[name + ".gk_w"], P[name + ".gk_b"], kg)
-        lib.dwpool(x, None, bt, g.h, g.w, self.gd, g.gh, g.gw, P[name + ".gv_w"], P[name + ".gv_b"], vg)
-        # LayerNorm statistics of window rows and of the pooled rows (attention_flow.py:142-143,154)
+        # pooled global tokens (attention_flow.py:135,145) and the LayerNorm statistics of window rows and pooled
+        # rows (attention_flow.py:142-143,154): one launch
         nl = g.nwp * 64
-        lib.rownorm(x, fp, qkn, gather=g.win_map, rows_per_batch=nl, total_rows=bt * nl, dst_batch_rows=g.R,
-                    eps=LN_EPS)
-        lib.rownorm(kg, None, qkn, rows_per_batch=g.G, total_rows=bt * g.G, dst_batch_rows=g.R, dst_row0=nl,
-                    eps=LN_EPS)
-        lib.rownorm(x, None, vn, gather=g.win_map, rows_per_batch=nl, total_rows=bt * nl, dst_batch_rows=g.R,
-                    eps=LN_EPS)
-        lib.rownorm(vg, None, vn, rows_per_batch=g.G, total_rows=bt * g.G, dst_batch_rows=g.R, dst_row0=nl,
-                    eps=LN_EPS)
+        lib.swin_prep(x, fp, bt, g.h, g.w, g.win_map, nl, g.R, self.gd, g.gh, g.gw, P[name + ".gk_w"],
+                      P[name + ".gk_b"], P[name + ".gv_w"], P[name + ".gv_b"], qkn, vn, eps=LN_EPS, tag=name)
         # Q | K from the 768-wide normalised rows, V from the 512-wide ones: two GEMMs into one [rows, 3d] buffer
         self._linear([lib.ASeg(qkn, d + df, bt * g.R)], P[name + ".qk"], bt * g.R, out_split=qkv, os_x=3 * d)
         self._linear([lib.ASeg(vn, d, bt * g.R)], P[name + ".v"], bt * g.R, out_split=qkv, os_x=3 * d,
@@ -684,16 +684,20 @@ class FGT(nn.Module):
                    seg_counts=[256, 256])
         # ---- flow encoder (model.py:206-212)
         lib._scope[-1] = "flow_encoder"
-        fcol = B("f_col", (bt, H, W, 64), split=True)
+        # 1-term mode: the branch's activations are single-plane fp16 tensors; 3-term mode: split-bf16 like the rest
+        fkw = dict(dtype=torch.float16) if _FLOW_TERMS == 1 else dict(split=True)
+        okey = "out_f16" if _FLOW_TERMS == 1 else "out_split"
+        fcol = B("f_col", (bt, H, W, 64), **fkw)
         lib.im2col_nchw(fl, None, fcol, k=5, stride=1, pad=2, replicate=True, OH=H, OW=W, tag="fenc1")
-        f1 = B("f1", (bt, H, W, 64), split=True)
-        f2 = B("f2", (bt, H2, W2, 128), split=True)
-        f3 = B("f3", (bt, H2, W2, 128), split=True)
-        f4 = B("f4", (bt, OH, OW, 128), split=True)
-        self._linear([lib.ASeg(fcol, 64, bt * H * W)], P["fenc1"], bt * H * W, act=lib.ACT_LEAKY02, out_split=f1)
-        self._conv(f1, 64, bt, H, W, P["fenc2"], 3, stride=2, out_split=f2)
-        self._conv(f2, 128, bt, H2, W2, P["fenc3"], 3, out_split=f3)
-        self._conv(f3, 128, bt, H2, W2, P["fenc4"], 3, stride=2, out_split=f4)
+        f1 = B("f1", (bt, H, W, 64), **fkw)
+        f2 = B("f2", (bt, H2, W2, 128), **fkw)
+        f3 = B("f3", (bt, H2, W2, 128), **fkw)
+        f4 = B("f4", (bt, OH, OW, 128), **fkw)
+        self._linear([lib.ASeg(fcol, 64, bt * H * W)], P["fenc1"], bt * H * W, act=lib.ACT_LEAKY02, terms=_FLOW_TERMS,
+                     **{okey: f1})
+        self._conv(f1, 64, bt, H, W, P["fenc2"], 3, stride=2, terms=_FLOW_TERMS, **{okey: f2})
+        self._conv(f2, 128, bt, H2, W2, P["fenc3"], 3, terms=_FLOW_TERMS, **{okey: f3})
+        self._conv(f3, 128, bt, H2, W2, P["fenc4"], 3, stride=2, terms=_FLOW_TERMS, **{okey: f4})
         # ---- patch embedding (model.py:261-262,270-271): conv output NHWC == token-major
         lib._scope[-1] = "patch_embed"
         rows = bt * g.n
@@ -705,7 +709,7 @@ class FGT(nn.Module):
         k, s, p = self.ksz[0], self.stride[0], self.padding[0]
         self._conv(enc, 128, bt, OH, OW, P["patch2vec"], k, stride=s, pad=p, act=lib.ACT_NONE, out_f32=xa)
         self._conv(f4, 128, bt, OH, OW, P["f_patch2vec"], k, stride=s, pad=p, act=lib.ACT_NONE, out_f32=f,
-                   out_split=fs)
+                   out_split=fs, terms=_FLOW_TERMS)
         self._cap("enc", enc_f)
         self._cap("tok0", xa)
         self._cap("ftok", f)

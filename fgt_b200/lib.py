@@ -38,7 +38,8 @@ class FgtGemmDesc(ctypes.Structure):
                 ("aux", _c_p), ("aux_mode", ctypes.c_int),
                 ("out_f32", _c_p), ("out_hi", _c_p), ("out_plane", _c_ll),
                 ("os_z", _c_ll), ("os_y", _c_ll), ("os_x", _c_ll), ("os_c", _c_ll),
-                ("rowmap", _c_p), ("lin_batch", ctypes.c_int), ("aux2", _c_p)]
+                ("rowmap", _c_p), ("lin_batch", ctypes.c_int), ("aux2", _c_p), ("terms", ctypes.c_int),
+                ("out_half", ctypes.c_int)]
 
 
 class FgtAttnDesc(ctypes.Structure):
@@ -117,6 +118,9 @@ def load():
     lib.fgt_tapsum.argtypes = [_c_p, ci, ci, ci, ci, ci, ci, ci, ci, cll, _c_p, ci, _c_p, cll, cll, cll, cll, _c_p]
     lib.fgt_tapsum.restype = ctypes.c_int
     lib.fgt_dwpool.argtypes = [_c_p, ci, _c_p, ci, ci, ci, ci, ci, ci, ci, _c_p, _c_p, _c_p, _c_p]
+    lib.fgt_swin_prep.argtypes = [_c_p, _c_p, ci, ci, ci, ci, ci, _c_p, ci, ci, ci, ci, ci, _c_p, _c_p, _c_p, _c_p, _c_p,
+                                  cll, _c_p, cll, cf, _c_p]
+    lib.fgt_swin_prep.restype = ctypes.c_int
     lib.fgt_dwconv3x3_res.argtypes = [_c_p, ci, ci, ci, ci, _c_p, _c_p, _c_p, _c_p, cll, _c_p]
     lib.fgt_fold.argtypes = [_c_p, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, _c_p, _c_p, _c_p, cll, _c_p]
     lib.fgt_unfold.argtypes = [_c_p, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, _c_p, cll, _c_p]
@@ -264,8 +268,9 @@ class ASeg:
 def gemm_tc(segs, w_split, N, *, kx=1, ky=1, kz=1, stride=1, dil=1, pad_x=0, pad_y=0, pad_z=0, groups=1,
             out_w, out_h=1, out_z=1, box_w=128, box_h=1, bn=128, bias=None, alpha=1.0, act=ACT_NONE,
             aux=None, aux_mode=AUX_NONE, out_f32=None, out_split=None, out_elem_offset=0,
-            os_z=0, os_y=0, os_x=None, os_c=1, rowmap=None, lin_batch=0, aux2=None, tag=""):
-    """Generic launcher for fgt_gemm_tc. Output strides are in elements; see include/fgt_b200.h."""
+            os_z=0, os_y=0, os_x=None, os_c=1, rowmap=None, lin_batch=0, aux2=None, terms=3, out_f16=None, tag=""):
+    """Generic launcher for fgt_gemm_tc. Output strides are in elements; see include/fgt_b200.h.
+    terms=1: the A segments' tensors and w_split are plain fp16 tensors (one plane); out_f16: plain fp16 output."""
     lib = load()
     d = FgtGemmDesc()
     d.num_segs = len(segs)
@@ -273,7 +278,7 @@ def gemm_tc(segs, w_split, N, *, kx=1, ky=1, kz=1, stride=1, dil=1, pad_x=0, pad
     for i, s in enumerate(segs):
         a = d.seg[i]
         a.hi = s.split.data_ptr() + 2 * s.elem_offset
-        a.plane = plane_elems(s.split)
+        a.plane = plane_elems(s.split) if terms != 1 else 0
         a.C, a.DX, a.DY, a.DZ = s.C, s.DX, s.DY, s.DZ
         a.sx, a.sy, a.sz = s.sx, s.sy, s.sz
         a.c_base, a.c_per_group, a.c_count = s.c_base, s.c_per_group, s.c_count
@@ -281,7 +286,8 @@ def gemm_tc(segs, w_split, N, *, kx=1, ky=1, kz=1, stride=1, dil=1, pad_x=0, pad
     d.kx, d.ky, d.kz, d.stride, d.dil = kx, ky, kz, stride, dil
     d.pad_x, d.pad_y, d.pad_z = pad_x, pad_y, pad_z
     d.w_hi = w_split.data_ptr()
-    d.w_plane = plane_elems(w_split)
+    d.w_plane = plane_elems(w_split) if terms != 1 else 0
+    assert (w_split.dtype == torch.float16) == (terms == 1), "terms=1 takes fp16 weights, terms=3 split-bf16 ones"
     d.N = N
     d.k_pad = w_split.shape[-1]
     d.groups = groups
@@ -297,10 +303,16 @@ def gemm_tc(segs, w_split, N, *, kx=1, ky=1, kz=1, stride=1, dil=1, pad_x=0, pad
     if out_split is not None:
         d.out_hi = out_split.data_ptr() + 2 * out_elem_offset
         d.out_plane = plane_elems(out_split)
+    if out_f16 is not None:
+        assert out_split is None and out_f16.dtype == torch.float16
+        d.out_hi = out_f16.data_ptr() + 2 * out_elem_offset
+        d.out_plane = 0
+        d.out_half = 1
     d.os_z, d.os_y, d.os_c = os_z, os_y, os_c
     d.os_x = N if os_x is None else os_x
     d.rowmap = rowmap.data_ptr() if rowmap is not None else None
     d.lin_batch = lin_batch
+    d.terms = terms
     # algorithmic work: every valid output position x N x (taps * real input channels), padding excluded
     m = out_w * out_h * out_z
     kk = kx * ky * kz * k_real
@@ -351,9 +363,11 @@ def im2col_nchw(src0, src1, out_split, *, k, stride, pad, replicate, OH, OW, sca
     n, c0, H, W = src0.shape
     c1 = src1.shape[1] if src1 is not None else 0
     cpad = out_split.shape[-1]
-    with _Prof("im2col_nchw", tag, 0, 4.0 * n * (c0 + c1) * H * W + 4.0 * out_split[0].numel()):
+    half = out_split.dtype == torch.float16  # plain fp16 rows [n, OH, OW, cpad] for a 1-term layer
+    nbytes = 4.0 * n * (c0 + c1) * H * W + (2.0 * out_split.numel() if half else 4.0 * out_split[0].numel())
+    with _Prof("im2col_nchw", tag, 0, nbytes):
         check(load().fgt_im2col_nchw(_dp(src0), c0, _dp(src1), c1, n, H, W, k, stride, pad, 1 if replicate else 0,
-                                     OH, OW, cpad, scale, shift, _dp(out_split), plane_elems(out_split),
+                                     OH, OW, cpad, scale, shift, _dp(out_split), 0 if half else plane_elems(out_split),
                                      stream_ptr()),
               "fgt_im2col_nchw")
 
@@ -406,6 +420,18 @@ def dwpool(a, b, bt, h, w, k, gh, gw, weight, bias, out, tag=""):
     with _Prof("dwpool", tag, 0, 4.0 * bt * (h * w + gh * gw) * (ca + cb)):
         check(load().fgt_dwpool(_dp(a), ca, _dp(b), cb, bt, h, w, k, gh, gw, _dp(weight), _dp(bias), _dp(out),
                                 stream_ptr()), "fgt_dwpool")
+
+
+def swin_prep(x, fp, bt, h, w, win_map, nl, R, gd, gh, gw, gk_w, gk_b, gv_w, gv_b, qkn, vn, eps=1e-5, tag=""):
+    """SWMHSA operand preparation in one launch: LayerNorm'd window rows and pooled global rows of [x ; f'] -> qkn
+    and of x -> vn (split-bf16 [bt*R, .]); see include/fgt_b200.h."""
+    d, df = x.shape[-1], fp.shape[-1]
+    G = gh * gw
+    nbytes = 4.0 * bt * ((nl + 2 * h * w) * (d + df) + (nl + G) * (2 * d + df))  # reads (rows + pooling) + split writes
+    with _Prof("swin_prep", tag, 0, nbytes):
+        check(load().fgt_swin_prep(_dp(x), _dp(fp), d, df, bt, h, w, _dp(win_map), nl, R, gd, gh, gw, _dp(gk_w),
+                                   _dp(gk_b), _dp(gv_w), _dp(gv_b), _dp(qkn), plane_elems(qkn), _dp(vn),
+                                   plane_elems(vn), eps, stream_ptr()), "fgt_swin_prep")
 
 
 def dwconv3x3_res(x, bt, h, w, C, weight, bias, out, out_split=None, tag=""):

@@ -16,11 +16,11 @@ def pad64(c):
     return (c + KB - 1) // KB * KB
 
 
-def pack_weight(w, seg_counts=None):
+def pack_weight(w, seg_counts=None, half=False):
     """w: [N, Cin_per_group, *taps] (torch conv layout; taps = (), (kh,kw) or (kt,kh,kw)).
 
     seg_counts: channels per group taken from each A segment (sum == Cin_per_group).
-    Returns split-bf16 tensor [2, N, k_pad].
+    Returns split-bf16 tensor [2, N, k_pad], or a plain fp16 [N, k_pad] for a 1-term layer (half=True).
     """
     w = w.detach().float()
     n, cin = w.shape[0], w.shape[1]
@@ -40,7 +40,7 @@ def pack_weight(w, seg_counts=None):
         blocks.append(blk)
         c0 += c
     packed = torch.cat(blocks, dim=2).reshape(n, -1).contiguous()
-    return to_split(packed)
+    return packed.to(torch.float16) if half else to_split(packed)
 
 
 def fold_layernorm(weight, bias, gamma, beta):
@@ -54,12 +54,12 @@ def fold_layernorm(weight, bias, gamma, beta):
     return w2.float(), b2.float()
 
 
-def pack_weight_im2col(w, cpad=KB):
+def pack_weight_im2col(w, cpad=KB, half=False):
     """Conv weight [N, cin, k, k] for a layer whose input was gathered by fgt_im2col_nchw:
     K index = (ky*k + kx)*cin + c, zero-padded to cpad."""
     w = w.detach().float()
     n = w.shape[0]
     flat = w.permute(0, 2, 3, 1).reshape(n, -1)
     assert flat.shape[1] <= cpad
-    flat = torch.nn.functional.pad(flat, (0, cpad - flat.shape[1]))
-    return to_split(flat.contiguous())
+    flat = torch.nn.functional.pad(flat, (0, cpad - flat.shape[1])).contiguous()
+    return flat.to(torch.float16) if half else to_split(flat)

@@ -197,9 +197,24 @@ def blend_frames(backend, video, gx, gy, mask, mask_gradient):
 
     _per_frame(fill, N)
     todo = [i for i in range(N) if mask[:, :, i].sum() > 0]
-    blends = backend.poisson_frames([video[:, :, :, i] for i in todo], [gx[:, 0:W - 1, :, i] for i in todo],
-                                    [gy[0:H - 1, :, :, i] for i in todo], [mask[:, :, i] for i in todo],
-                                    [mask_gradient[:, :, i] for i in todo]) if todo else []
+
+    def solve(ids):
+        return backend.poisson_frames([video[:, :, :, i] for i in ids], [gx[:, 0:W - 1, :, i] for i in ids],
+                                      [gy[0:H - 1, :, :, i] for i in ids], [mask[:, :, i] for i in ids],
+                                      [mask_gradient[:, :, i] for i in ids])
+
+    # The driver wraps each frame's blend in try/except and falls back to (video_comp[..., i], mask[..., i]) (:648-660).
+    # The batched solve is retried frame by frame when it fails, so one bad frame cannot take the clip down.
+    blends = []
+    if todo:
+        try:
+            blends = solve(todo)
+        except Exception:  # noqa: BLE001 - mirrors the driver's bare except
+            for i in todo:
+                try:
+                    blends.append(solve([i])[0])
+                except Exception:  # noqa: BLE001
+                    blends.append((video[:, :, :, i].astype(np.float64), mask[:, :, i].copy()))
     slot = {i: k for k, i in enumerate(todo)}
 
     def finish(i):
@@ -260,15 +275,27 @@ class GpuBackend:
         from .propagation import get_flowNN_gradient
         return get_flowNN_gradient(args, gx, gy, mask, mask_gradient, flow_f, flow_b, None, None, device=str(self.dev))
 
+    POISSON_BYTES_PER_PIXEL = 364   # fp64 solver state (u, v, w, x, target, result) + the 2*H*W per-iteration scalar slots
+    POISSON_BUDGET_BYTES = 8 << 30  # frames per batch are bounded by this much device memory (results are per-frame independent)
+
     def poisson_frames(self, trg, gx, gy, hole, gmask):
         from .poisson import poisson_blend_batch
         st = lambda xs: np.ascontiguousarray(np.stack(xs, 0))
-        trg = st(trg)
-        out, unf = poisson_blend_batch(trg, st(gx), st(gy), st(hole), st(gmask), device=self.dev)
-        if trg.dtype == np.float32:      # every value of the blend is then a float32 (float64(float32(x)) in the hole, the
-            out = out.float()            # float32 target outside): half the bytes back over the bus, widened exactly on the host
-        out, unf = out.cpu().numpy().astype(np.float64), unf.cpu().numpy()
-        return [(out[i], unf[i]) for i in range(out.shape[0])]
+        n = len(trg)
+        if n == 0:
+            return []
+        H, W = trg[0].shape[:2]
+        per = max(1, int(self.POISSON_BUDGET_BYTES // (self.POISSON_BYTES_PER_PIXEL * H * W)))
+        res = []
+        for s in range(0, n, per):
+            e = min(n, s + per)
+            t = st(trg[s:e])
+            out, unf = poisson_blend_batch(t, st(gx[s:e]), st(gy[s:e]), st(hole[s:e]), st(gmask[s:e]), device=self.dev)
+            if t.dtype == np.float32:    # every value of the blend is then a float32 (float64(float32(x)) in the hole, the
+                out = out.float()        # float32 target outside): half the bytes back over the bus, widened exactly on the host
+            out, unf = out.cpu().numpy().astype(np.float64), unf.cpu().numpy()
+            res += [(out[i], unf[i]) for i in range(out.shape[0])]
+        return res
 
     def fgt_stage(self, frame_blends, mask, flow_f, step, num_ref, neighbor_stride):
         from .clip import inpaint_clip

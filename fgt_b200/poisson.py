@@ -14,7 +14,7 @@ import torch
 from . import lib
 
 CHUNK = 48            # iterations per graph replay = between convergence checks (one host sync each)
-MAX_ITERS = 20000     # cap on the slot arrays; the reference's own limit is 2*H*W
+MAX_ITERS = None      # None: scipy's own limit iter_lim = 2*H*W (then istop = 7 and the iterate is returned as is)
 
 
 def _dev(device):
@@ -63,7 +63,10 @@ def poisson_blend_batch(trg, gx, gy, hole, gmask=None, edge=None, device=None, r
     code = torch.zeros(F, H, W, dtype=torch.uint8, device=dev)
     u = z64(F, 4, H * W, C)
     v, w, x = z64(F, H * W, C), z64(F, H * W, C), z64(F, H * W, C)
-    slots = max_iters + CHUNK + 2                      # a replay may run past the last stop by < CHUNK (frozen) iterations
+    iter_lim = 2 * H * W                               # scipy.sparse.linalg.lsqr's default for an [m, H*W] system
+    if max_iters is None:
+        max_iters = iter_lim                           # the device-side test k >= iter_lim stops every system by then
+    slots = min(max_iters, iter_lim) + CHUNK + 2       # a replay may run past the last stop by < CHUNK (frozen) iterations
     bb, aa, ww = z64(slots * S), z64(slots * S), z64(slots * S)
     state = z64(2, S, 16)
     plist = torch.zeros(F, H * W, dtype=torch.int32, device=dev)    # uint32 entries: pixel | code << 24, 0 = none
@@ -77,7 +80,6 @@ def poisson_blend_batch(trg, gx, gy, hole, gmask=None, edge=None, device=None, r
     clr = torch.empty(2, F, H, W, dtype=torch.uint8, device=dev)
     lib.check(L.fgt_poisson_unfilled(hole.data_ptr(), _ptr(gmask), F, H, W, clr.data_ptr(), sp()), "fgt_poisson_unfilled")
     lib.COUNTERS["launches"] += 2
-    iter_lim = 2 * H * W
     max_cnt = int(cnt.max())                           # pixels owning equations, largest frame (one host sync)
     iter_args = (plist.data_ptr(), max_cnt, F, H, W, u.data_ptr(), v.data_ptr(), w.data_ptr(), x.data_ptr(),
                  bb.data_ptr(), aa.data_ptr(), ww.data_ptr(), state.data_ptr(), kctr.data_ptr(), CHUNK, atol, btol,
@@ -88,7 +90,7 @@ def poisson_blend_batch(trg, gx, gy, hole, gmask=None, edge=None, device=None, r
     k = 0
     try:
         while True:
-            if k > max_iters:
+            if k > min(max_iters, iter_lim) + CHUNK:   # cannot happen with max_iters = iter_lim (istop = 7 by then)
                 raise RuntimeError(f"poisson: LSQR did not stop within {max_iters} iterations")
             if use_graph:
                 lib.check(L.fgt_poisson_graph_launch(exec_, sp()), "fgt_poisson_graph_launch")

@@ -10,7 +10,7 @@ import torch
 from . import lib
 
 CHUNK = 64           # iterations between convergence checks (one host sync each)
-MAX_ITERS = 10000
+MAX_ITERS = None     # None: max(10000, 50 * (H + W)) — CG on a hole of diameter d needs ~25 d iterations at tol 1e-12
 
 
 def regionfill_batch(images, masks, tol=1e-12, device=None, return_iters=False, max_iters=MAX_ITERS):
@@ -24,6 +24,8 @@ def regionfill_batch(images, masks, tol=1e-12, device=None, return_iters=False, 
     if img.dim() != 3 or img.shape != msk.shape:
         raise ValueError(f"regionfill: images {tuple(img.shape)} and masks {tuple(msk.shape)} must both be [B,H,W]")
     B, H, W = img.shape
+    if max_iters is None:
+        max_iters = max(10000, 50 * (H + W))
     full = msk.flatten(1).all(dim=1)
     if bool(full.any()):
         raise ValueError("regionfill: a mask covers its whole image (singular system; the reference fails too)")

@@ -106,6 +106,10 @@ typedef struct {
   const int* rowmap;         /* linear mode only (out_h == out_z == 1): row -> output row, <0 = drop */
   int lin_batch;             /* linear mode: if >0, z = row / lin_batch, x = row % lin_batch */
   const float* aux2;         /* second fp32 operand (FGT_AUX_GRU: the update gate z), addressed like the output */
+  int terms;                 /* 0 / 3: split-bf16 product hi*hi + hi*lo + lo*hi (fp32-grade, 3 MMAs per K step);
+                                1: the A segments and W are single-plane fp16 tensors (`hi` points at fp16 data, the
+                                plane offsets are ignored), one MMA per K step — for layers whose error budget allows */
+  int out_half;              /* 1: out_hi receives ONE plane of fp16 (the input format of a terms == 1 layer) */
 } FgtGemmDesc;
 
 int fgt_gemm_tc(const FgtGemmDesc* desc, fgt_stream_t stream);
@@ -311,6 +315,19 @@ int fgt_tapsum(const float* y, int n, int H, int W, int cout, int kx, int ky, in
  * Replaces global_extract_k / global_extract_v, attention_flow.py:135,145. */
 int fgt_dwpool(const float* a, int ca, const float* b, int cb, int bt, int h, int w, int k, int gh, int gw,
                const float* weight, const float* bias, float* out, fgt_stream_t stream);
+
+/* Operand preparation of SWMHSA in one launch (attention_flow.py:130-154): for every frame, the LayerNorm statistics
+ * (no affine: q_norm / k_norm / v_norm are folded into the projection weights) of the window-partitioned tokens
+ * [x ; f'] (d+df channels -> qkn) and x (d channels -> vn), then of the pooled global tokens (depthwise gd x gd /
+ * stride gd convolution + bias of [x ; f'] with gk_* and of x with gv_*; the depthwise weights are passed TAP-MAJOR,
+ * [gd*gd, C] = torch's [C,1,gd,gd] transposed, so that one tap's weights are a coalesced row).
+ * Destination rows per frame: [0, nl) window rows through win_map (token index, <0 = zero row), [nl, nl + gh*gw)
+ * pooled rows; R rows per frame in total. qkn / vn are split-bf16 [bt*R, d+df] / [bt*R, d]. Replaces two fgt_dwpool
+ * and four fgt_rownorm launches. */
+int fgt_swin_prep(const float* x, const float* fp, int d, int df, int bt, int h, int w, const int* win_map, int nl,
+                  int R, int gd, int gh, int gw, const float* gk_w, const float* gk_b, const float* gv_w,
+                  const float* gv_b, void* qkn_hi, long long qkn_plane, void* vn_hi, long long vn_plane, float eps,
+                  fgt_stream_t stream);
 
 /* out = x + depthwise3x3(x) + bias on the token grid (AddPosEmb.forward, model.py:75-88). */
 int fgt_dwconv3x3_res(const float* x, int bt, int h, int w, int C, const float* weight, const float* bias,

@@ -41,6 +41,64 @@ def test_conv(kw):
     assert D.conv_case(**kw)
 
 
+@pytest.mark.parametrize("kw", [
+    dict(M=7200, N=1960, K=512, bn=128),                                              # fp32 only, N tail clipped by TMA
+    dict(M=1000, N=520, K=1960, bn=128, act=2, split_only=True, aux_mode=1),          # split only, M and N tails, residual
+    dict(M=7200, N=1536, K=512, bn=128, split_only=True),
+    dict(M=333, N=256, K=320, bn=256, split_only=True, act=3, aux_mode=2),
+    dict(M=7200, N=256, K=768, bn=128, terms=1, split_only=True),                     # fp16 operands, fp16 output
+    dict(M=1000, N=192, K=576, bn=64, terms=1, act=1),                                # fp16 operands, fp32 output
+    dict(M=2000, N=256, K=6272, bn=128, terms=1, split_out=True),                     # f_patch2vec: fp32 + split outputs
+    dict(M=70000, N=64, K=64, bn=64, split_only=True, act=1),                         # one K iteration per tile (8 TMEM buffers)
+])
+def test_linear_tma_epilogue_and_one_term(kw):
+    """Launches with a single, channel-contiguous output store through shared memory + TMA tile stores; terms=1 uses
+    single-plane fp16 operands (the flow branch)."""
+    from tools import diag_gemm as D
+    assert D.linear_case(**kw)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(n=2, h=61, w=107, cin=64, cout=128, k=3, stride=2, bn=128, split_only=True),  # edge tiles clipped by the TMA store
+    dict(n=2, h=60, w=108, cin=128, cout=128, k=3, bn=128, terms=1, split_only=True),
+    dict(n=1, h=30, w=54, cin=192, cout=192, k=3, dil=4, bn=64, split_only=True),
+])
+def test_conv_tma_epilogue_and_one_term(kw):
+    from tools import diag_gemm as D
+    assert D.conv_case(**kw)
+
+
+def test_tma_epilogue_bit_equal_to_register_epilogue():
+    """The two epilogue paths run the same arithmetic: identical bits."""
+    import ctypes
+    lib = _lib()
+    from fgt_b200 import packing
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    M, N, K = 1500, 712, 320
+    a_s = lib.to_split(torch.randn(M, K, device=dev))
+    w_s = packing.pack_weight(torch.randn(N, K, device=dev) / K ** 0.5).to(dev)
+    b = torch.randn(N, device=dev)
+    aux = torch.randn(M, N, device=dev)
+    L = lib.load()
+    L.fgt_debug_gemm_direct_epilogue.argtypes = [ctypes.c_int]
+    outs = []
+    for direct in (0, 1):
+        L.fgt_debug_gemm_direct_epilogue(direct)
+        try:
+            o32 = torch.zeros(M, N, device=dev)
+            osp = torch.zeros(2, M, N, dtype=torch.bfloat16, device=dev)
+            lib.gemm_tc([lib.ASeg(a_s, K, M)], w_s, N, out_w=M, bn=128, bias=b, act=lib.ACT_LEAKY02, out_f32=o32, aux=aux,
+                        aux_mode=lib.AUX_ADD)
+            lib.gemm_tc([lib.ASeg(a_s, K, M)], w_s, N, out_w=M, bn=128, bias=b, act=lib.ACT_LEAKY02, out_split=osp,
+                        aux=aux, aux_mode=lib.AUX_ADD)
+            torch.cuda.synchronize()
+        finally:
+            L.fgt_debug_gemm_direct_epilogue(0)
+        outs.append((o32, osp))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 def test_linear_rowmap_and_transposed_store():
     lib = _lib()
     from fgt_b200 import packing
@@ -192,3 +250,56 @@ def test_taps_as_n_conv(n, H, W, cin, cout, act, nchw):
     lib.tapsum(y, n, H, W, cout, 3, b, act, out, nchw=nchw)
     got = out if nchw else out.permute(0, 3, 1, 2)
     assert_close(got, ref, KTOL, "taps-as-N conv")
+
+
+@pytest.mark.parametrize("bt,h,w", [(2, 20, 36), (1, 22, 36), (1, 7, 13)])
+def test_swin_prep_vs_torch(bt, h, w):
+    """fgt_swin_prep = zero-pad + window partition + depthwise pooling + the two LayerNorm statistics of SWMHSA's
+    operand preparation (attention_flow.py:122-154), against an fp64 PyTorch restatement."""
+    lib = _lib()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(4)
+    d, df, ws, gd = 512, 256, 8, 4
+    x = torch.randn(bt * h * w, d, device=dev) * 2 + 0.3
+    fp = torch.randn(bt * h * w, df, device=dev)
+    Hn, Wn = h + (ws - h % ws) % ws, w + (ws - w % ws) % ws
+    nwin = (Hn // ws) * (Wn // ws)
+    nwp = (nwin + 1) // 2 * 2
+    gh, gw = Hn // gd, Wn // gd
+    G = gh * gw
+    R = nwp * 64 + (G + 63) // 64 * 64
+    nl = nwp * 64
+    f, wy, wx, py, px = torch.meshgrid(torch.arange(bt), torch.arange(Hn // ws), torch.arange(Wn // ws), torch.arange(ws),
+                                       torch.arange(ws), indexing="ij")
+    Y, X = wy * ws + py, wx * ws + px
+    tok = torch.where((Y < h) & (X < w), (f * h + Y) * w + X, torch.full_like(Y, -1)).reshape(bt, nwin * 64)
+    full = torch.full((bt, nl), -1, dtype=tok.dtype)
+    full[:, :nwin * 64] = tok
+    win_map = full.reshape(-1).to(torch.int32).to(dev)
+    gk_w, gk_b = torch.randn(d + df, 1, gd, gd, device=dev) * 0.3, torch.randn(d + df, device=dev)
+    gv_w, gv_b = torch.randn(d, 1, gd, gd, device=dev) * 0.3, torch.randn(d, device=dev)
+    qkn = torch.full((2, bt * R, d + df), 7.0, dtype=torch.bfloat16, device=dev)
+    vn = torch.full((2, bt * R, d), 7.0, dtype=torch.bfloat16, device=dev)
+    lib.swin_prep(x, fp, bt, h, w, win_map, nl, R, gd, gh, gw, gk_w.reshape(d + df, -1).t().contiguous(), gk_b,
+                  gv_w.reshape(d, -1).t().contiguous(), gv_b, qkn, vn)
+    torch.cuda.synchronize()
+    # reference
+    xg = F.pad(x.double().reshape(bt, h, w, d), (0, 0, 0, Wn - w, 0, Hn - h))
+    qg = F.pad(torch.cat([x, fp], 1).double().reshape(bt, h, w, d + df), (0, 0, 0, Wn - w, 0, Hn - h))
+
+    def windows(g):
+        c = g.shape[-1]
+        return g.reshape(bt, Hn // ws, ws, Wn // ws, ws, c).permute(0, 1, 3, 2, 4, 5).reshape(bt, nwin * 64, c)
+
+    kg = F.conv2d(qg.permute(0, 3, 1, 2), gk_w.double(), gk_b.double(), stride=gd, groups=d + df).permute(0, 2, 3, 1)
+    vg = F.conv2d(xg.permute(0, 3, 1, 2), gv_w.double(), gv_b.double(), stride=gd, groups=d).permute(0, 2, 3, 1)
+    got_q = lib.from_split(qkn).reshape(bt, R, d + df)
+    got_v = lib.from_split(vn).reshape(bt, R, d)
+    valid = (tok >= 0).to(dev)
+    ref_q = F.layer_norm(windows(qg), (d + df,)) * valid[..., None]   # rows of the zero padding are written as zeros
+    ref_v = F.layer_norm(windows(xg), (d,)) * valid[..., None]
+    assert_close(got_q[:, :nwin * 64], ref_q, KTOL, "swin_prep window rows (q|k)")
+    assert_close(got_v[:, :nwin * 64], ref_v, KTOL, "swin_prep window rows (v)")
+    assert_close(got_q[:, nl:nl + G], F.layer_norm(kg.reshape(bt, G, d + df), (d + df,)), KTOL, "swin_prep pooled rows (k)")
+    assert_close(got_v[:, nl:nl + G], F.layer_norm(vg.reshape(bt, G, d), (d,)), KTOL, "swin_prep pooled rows (v)")
+    assert (got_q[:, nwin * 64:nl] == 0).all() and (got_q[:, nl + G:] == 14.0).all()   # dummy window zeroed, pad rows untouched

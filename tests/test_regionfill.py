@@ -42,7 +42,7 @@ def test_gpu_regionfill_vs_golden_and_oracle(name):
     img, mask = synth.regionfill_inputs(seed=seed, B=B, H=H, W=W)
     out, iters = RF.regionfill_batch(img, mask, return_iters=True)
     out = out.cpu().numpy()
-    assert out.dtype == np.float64 and 0 < iters < RF.MAX_ITERS
+    assert out.dtype == np.float64 and 0 < iters < 10000
     assert np.array_equal(out[~mask], img.astype(np.float64)[~mask])          # untouched outside the holes
     assert np.abs(out[mask] - g["out_hole"]).max() < 1e-7, "vs reference golden"
     ora = np.stack([RO.regionfill(img[b], mask[b]) for b in range(B)])

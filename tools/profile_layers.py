@@ -25,7 +25,7 @@ tot = 0.0
 print(f"{'kernel':14s} {'tag':14s} {'ms':>8s} {'TFLOP/s':>9s} {'GB/s':>8s}")
 for i in range(n):
     ms = sum(recs[i + r * n][4] for r in range(reps)) / reps
-    k, tag, fl, by, _ = recs[i]
+    k, tag, fl, by, _, _sc = recs[i]
     tot += ms
     tf = fl / (ms * 1e-3) / 1e12 if fl else 0.0
     gb = by / (ms * 1e-3) / 1e9
