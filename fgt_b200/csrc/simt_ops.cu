@@ -253,15 +253,18 @@ __global__ void dwconv3_res_kernel(const float* __restrict__ x, int bt, int h, i
                                    float* __restrict__ out, __nv_bfloat16* __restrict__ hi, long long plane) {
   pdl_launch_dependents();
   pdl_wait();
-  const long long total = static_cast<long long>(bt) * h * w * C;
+  // one thread = 4 consecutive channels of one token: float4 loads of the 3x3 neighbourhood (coalesced along c)
+  const int C4 = C / 4;
+  const long long total = static_cast<long long>(bt) * h * w * C4;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % C);
-    const long long t = i / C;
+    const int c = static_cast<int>(i % C4) * 4;
+    const long long t = i / C4;
     const int px = static_cast<int>(t % w);
     const int py = static_cast<int>((t / w) % h);
     const long long f = t / (static_cast<long long>(w) * h);
-    float acc = bias[c];
+    float4 acc = __ldg(reinterpret_cast<const float4*>(bias + c));
+    float4 centre = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int y = py + ky - 1;
@@ -270,17 +273,19 @@ __global__ void dwconv3_res_kernel(const float* __restrict__ x, int bt, int h, i
       for (int kx = 0; kx < 3; ++kx) {
         const int xx = px + kx - 1;
         if (xx < 0 || xx >= w) continue;
-        acc += wt[c * 9 + ky * 3 + kx] * x[((f * h + y) * w + xx) * C + c];
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + ((f * h + y) * w + xx) * C + c));
+        if (ky == 1 && kx == 1) centre = v;
+        const int tap = ky * 3 + kx;
+        acc.x += __ldg(wt + (c + 0) * 9 + tap) * v.x;
+        acc.y += __ldg(wt + (c + 1) * 9 + tap) * v.y;
+        acc.z += __ldg(wt + (c + 2) * 9 + tap) * v.z;
+        acc.w += __ldg(wt + (c + 3) * 9 + tap) * v.w;
       }
     }
-    const float v = acc + x[i];
-    out[i] = v;
-    if (hi) {
-      __nv_bfloat16 hh, ll;
-      split_bf16(v, hh, ll);
-      hi[i] = hh;
-      hi[plane + i] = ll;
-    }
+    const float4 v = make_float4(acc.x + centre.x, acc.y + centre.y, acc.z + centre.z, acc.w + centre.w);
+    const long long o = t * C + c;
+    *reinterpret_cast<float4*>(out + o) = v;
+    if (hi) store_split4(hi + o, hi + plane + o, v.x, v.y, v.z, v.w);
   }
 }
 
@@ -522,7 +527,8 @@ extern "C" int fgt_dwpool(const float* a, int ca, const float* b, int cb, int bt
 extern "C" int fgt_dwconv3x3_res(const float* x, int bt, int h, int w, int C, const float* weight, const float* bias,
                                  float* out, void* out_hi, long long out_plane, fgt_stream_t stream) {
   FGT_REQUIRE(x && weight && bias && out, FGT_ERR_ARG, "dwconv3x3_res: null argument");
-  const long long total = static_cast<long long>(bt) * h * w * C;
+  FGT_REQUIRE(C % 4 == 0, FGT_ERR_ARG, "dwconv3x3_res: C=%d must be a multiple of 4", C);
+  const long long total = static_cast<long long>(bt) * h * w * (C / 4);
   launch_k(dwconv3_res_kernel, dim3(grid_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
       x, bt, h, w, C, weight, bias, out, reinterpret_cast<__nv_bfloat16*>(out_hi), out_plane);
   FGT_CUDA(cudaGetLastError());

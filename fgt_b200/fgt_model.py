@@ -433,8 +433,9 @@ class FGT(nn.Module):
                             os_z=4 * h * w * N, os_y=4 * w * N, os_x=2 * N, os_c=1, tag=wp["name"])
 
     @staticmethod
-    def _linear(segs, wp, rows, **kw):
-        lib.gemm_tc(segs, wp["w"], wp["N"], out_w=rows, bn=_pick_bn(wp["N"], 1, wp["name"]), bias=wp["b"], tag=wp["name"], **kw)
+    def _linear(segs, wp, rows, bn=None, **kw):
+        lib.gemm_tc(segs, wp["w"], wp["N"], out_w=rows, bn=bn or _pick_bn(wp["N"], 1, wp["name"]), bias=wp["b"],
+                    tag=wp["name"], **kw)
 
     def _ffn(self, g, P, name, x, xs, dev):
         """x += FusionFeedForward(LN(x)) (ffn_base.py:53-77, model.py:128-129 / 147-148)."""
@@ -508,13 +509,15 @@ class FGT(nn.Module):
         lib.rownorm_bcast(x, ptrs, plane, gather=g.zone_map, rows_per_batch=Lzl, total_rows=g.zones * Lzl,
                           dst_batch_rows=Lz, dst_row0=off * zl, eps=LN_EPS, gamma=P[name + ".ln_g"],
                           beta=P[name + ".ln_b"])
-        pg.barrier()
-        # Q only for this rank's frames: rows [off*zl, off*zl + Lzl) of every zone, read in place (strided view)
+        # Q only for this rank's frames: rows [off*zl, off*zl + Lzl) of every zone, read in place (strided view). These
+        # rows were written by this rank's own LayerNorm launch (stream order), so the Q projection runs BEFORE the
+        # barrier and hides the time the peers' rows need to arrive over NVLink.
         wq = P[name + ".q"]
         bw, bh = _pick_box(Lzl, g.zones)
         lib.gemm_tc([lib.ASeg(s_all, d, Lzl, g.zones, 1, sx=d, sy=Lz * d, elem_offset=off * zl * d)], wq["w"], d,
                     out_w=Lzl, out_h=g.zones, box_w=bw, box_h=bh, bn=_pick_bn(d, 1, wq["name"]), bias=wq["b"],
                     out_split=q, os_x=d, os_y=Lzl * d, tag=wq["name"])
+        pg.barrier()  # every peer's rows of this layer are in s_all
         self._linear([lib.ASeg(s_all, d, g.zones * Lz)], P[name + ".kv"], g.zones * Lz, out_split=kv)
         lib.attention(q, kv, kv, att, batches=g.zones, heads=self.heads, Lq=Lzl, Lk=Lz, q_ld=d, k_ld=2 * d, v_ld=2 * d,
                       out_ld=d, q_batch_stride=Lzl * d, k_batch_stride=Lz * 2 * d, v_batch_stride=Lz * 2 * d,
@@ -603,7 +606,7 @@ class FGT(nn.Module):
         att = self._buf(g, "s_att", (bt * g.nwp * 64, d), dev, split=True)
         # flow re-weighting gate: f' = f * sigmoid(W_r [x; f] + b_r)   (attention_flow.py:126-128)
         self._linear([lib.ASeg(xs, d, rows), lib.ASeg(fs, df, rows)], P[name + ".gate"], rows, act=lib.ACT_SIGMOID,
-                     aux=f, aux_mode=lib.AUX_MUL, out_f32=fp)
+                     aux=f, aux_mode=lib.AUX_MUL, out_f32=fp, bn=64 if rows <= 128 * 74 else None)  # 114 -> 228 tiles
         # pooled global tokens (attention_flow.py:135,145) and the LayerNorm statistics of window rows and pooled
         # rows (attention_flow.py:142-143,154): one launch
         nl = g.nwp * 64
@@ -741,9 +744,8 @@ class FGT(nn.Module):
         self._deconv(feat, c2, bt, OH, OW, P, "dec1", d1)
         self._conv(d1, c2, bt, H2, W2, P["dec2"], 3, out_split=d2)
         self._deconv(d2, c2 // 2, bt, H2, W2, P, "dec3", d3)
-        y4 = B("dec4_y", (32, bt * H * W))  # column-planar partial products
-        self._linear([lib.ASeg(d3, c2 // 2, bt * H * W)], P["dec4t"], bt * H * W, out_f32=y4, os_x=1, os_c=bt * H * W)
-        lib.tapsum(y4, bt, H, W, 3, 3, P["dec4"]["b"], lib.ACT_TANH, out, nchw=True, tag="dec4")
+        # final 64 -> 3 conv + tanh: taps-as-N tensor-core GEMM and the 9-tap sum in one kernel (no HBM intermediate)
+        lib.conv_tail(d3, bt, H, W, c2 // 2, P["dec4t"]["w"], 3, P["dec4"]["b"], lib.ACT_TANH, out, nchw=True, tag="dec4")
         lib._scope[1:] = []
         return out
 

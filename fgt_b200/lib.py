@@ -118,6 +118,8 @@ def load():
     lib.fgt_tapsum.argtypes = [_c_p, ci, ci, ci, ci, ci, ci, ci, ci, cll, _c_p, ci, _c_p, cll, cll, cll, cll, _c_p]
     lib.fgt_tapsum.restype = ctypes.c_int
     lib.fgt_dwpool.argtypes = [_c_p, ci, _c_p, ci, ci, ci, ci, ci, ci, ci, _c_p, _c_p, _c_p, _c_p]
+    lib.fgt_conv_tail.argtypes = [_c_p, cll, ci, ci, ci, ci, _c_p, cll, ci, ci, _c_p, ci, _c_p, cll, cll, cll, cll, _c_p]
+    lib.fgt_conv_tail.restype = ctypes.c_int
     lib.fgt_swin_prep.argtypes = [_c_p, _c_p, ci, ci, ci, ci, ci, _c_p, ci, ci, ci, ci, ci, _c_p, _c_p, _c_p, _c_p, _c_p,
                                   cll, _c_p, cll, cf, _c_p]
     lib.fgt_swin_prep.restype = ctypes.c_int
@@ -420,6 +422,17 @@ def dwpool(a, b, bt, h, w, k, gh, gw, weight, bias, out, tag=""):
     with _Prof("dwpool", tag, 0, 4.0 * bt * (h * w + gh * gw) * (ca + cb)):
         check(load().fgt_dwpool(_dp(a), ca, _dp(b), cb, bt, h, w, k, gh, gw, _dp(weight), _dp(bias), _dp(out),
                                 stream_ptr()), "fgt_dwpool")
+
+
+def conv_tail(x_split, n, H, W, cin, w_split, cout, bias, act, out, *, nchw, tag=""):
+    """3x3 conv (pad 1) with cout <= 3 + bias + activation: x_split [2,n,H,W,cin] -> out [n,cout,H,W] (nchw) or
+    [n,H,W,cout] fp32, one kernel (taps-as-N GEMM + in-SM tap sum). w_split = pack_weight(pack_taps_as_n(w))."""
+    st = (cout * H * W, H * W, W, 1) if nchw else (H * W * cout, 1, W * cout, cout)
+    # 2*9*cout*cin FLOP per 4*(cin+cout) bytes = ~13 FLOP/B at 64 -> 3: HBM-bound, reported against the copy roofline
+    nbytes = 4.0 * n * H * W * (cin + cout)
+    with _Prof("conv_tail", tag, 0.0, nbytes):
+        check(load().fgt_conv_tail(_dp(x_split), plane_elems(x_split), n, H, W, cin, _dp(w_split), plane_elems(w_split),
+                                   w_split.shape[-1], cout, _dp(bias), act, _dp(out), *st, stream_ptr()), "fgt_conv_tail")
 
 
 def swin_prep(x, fp, bt, h, w, win_map, nl, R, gd, gh, gw, gk_w, gk_b, gv_w, gv_b, qkn, vn, eps=1e-5, tag=""):

@@ -316,6 +316,16 @@ int fgt_tapsum(const float* y, int n, int H, int W, int cout, int kx, int ky, in
 int fgt_dwpool(const float* a, int ca, const float* b, int cb, int bt, int h, int w, int k, int gh, int gw,
                const float* weight, const float* bias, float* out, fgt_stream_t stream);
 
+/* 3x3 convolution (zero padding 1, stride 1) with cout <= 3 output channels + bias + activation in one kernel: the
+ * nine taps become the N dimension of a tcgen05 GEMM over the input positions (activation read once) and are summed
+ * per output pixel in shared memory — the decoder's final conv + tanh (FGT/models/model.py:185-193). x: NHWC
+ * split-bf16 [n,H,W,cin], cin a multiple of 64 (<= 256); w: split-bf16 [32, cin], row tap*cout + c = W[c,:,ty,tx]
+ * (zero rows up to 32); out: fp32 with element strides (os_n, os_c, os_y, os_x). Replaces fgt_gemm_tc "taps as N" +
+ * fgt_tapsum and their column-planar intermediate. */
+int fgt_conv_tail(const void* x_hi, long long x_plane, int n, int H, int W, int cin, const void* w_hi, long long w_plane,
+                  int k_pad, int cout, const float* bias, int act, float* out, long long os_n, long long os_c,
+                  long long os_y, long long os_x, fgt_stream_t stream);
+
 /* Operand preparation of SWMHSA in one launch (attention_flow.py:130-154): for every frame, the LayerNorm statistics
  * (no affine: q_norm / k_norm / v_norm are folded into the projection weights) of the window-partitioned tokens
  * [x ; f'] (d+df channels -> qkn) and x (d channels -> vn), then of the pooled global tokens (depthwise gd x gd /

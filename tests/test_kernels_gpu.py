@@ -303,3 +303,28 @@ def test_swin_prep_vs_torch(bt, h, w):
     assert_close(got_q[:, nl:nl + G], F.layer_norm(kg.reshape(bt, G, d + df), (d + df,)), KTOL, "swin_prep pooled rows (k)")
     assert_close(got_v[:, nl:nl + G], F.layer_norm(vg.reshape(bt, G, d), (d,)), KTOL, "swin_prep pooled rows (v)")
     assert (got_q[:, nwin * 64:nl] == 0).all() and (got_q[:, nl + G:] == 14.0).all()   # dummy window zeroed, pad rows untouched
+
+
+@pytest.mark.parametrize("n,H,W,cin,cout,act", [(2, 24, 40, 64, 3, 4), (1, 21, 37, 128, 2, 0), (3, 240, 432, 64, 3, 4)])
+def test_conv_tail_vs_torch(n, H, W, cin, cout, act):
+    """fgt_conv_tail (taps-as-N GEMM + in-SM tap sum + bias + activation) against F.conv2d in fp64, edge tiles included."""
+    lib = _lib()
+    from fgt_b200 import packing
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    x = torch.randn(n, cin, H, W, device=dev)
+    w = torch.randn(cout, cin, 3, 3, device=dev) / (cin * 9) ** 0.5
+    b = torch.randn(cout, device=dev)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    if act == 4:
+        ref = torch.tanh(ref)
+    xs = lib.to_split(x.permute(0, 2, 3, 1).contiguous())
+    ws = packing.pack_weight(lib.pack_taps_as_n(w)).to(dev)
+    out = torch.full((n, cout, H, W), float("nan"), device=dev)
+    lib.conv_tail(xs, n, H, W, cin, ws, cout, b, act, out, nchw=True)
+    torch.cuda.synchronize()
+    assert_close(out, ref, KTOL, "conv_tail nchw")
+    out2 = torch.full((n, H, W, cout), float("nan"), device=dev)
+    lib.conv_tail(xs, n, H, W, cin, ws, cout, b, act, out2, nchw=False)
+    torch.cuda.synchronize()
+    assert_close(out2.permute(0, 3, 1, 2), ref, KTOL, "conv_tail nhwc")
