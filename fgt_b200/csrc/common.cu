@@ -7,6 +7,9 @@
 #include <cudaTypedefs.h>
 #include <stdarg.h>
 
+#include <mutex>
+#include <unordered_map>
+
 namespace fgt {
 
 static thread_local char g_err[512] = "";
@@ -40,8 +43,61 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// Descriptor cache: eager-mode callers (RAFT's 20-iteration loop, the pipeline) launch the same (pointer, shape)
+// combinations over and over; encoding is a driver call per map (2-19 maps per GEMM launch). Keyed by every encode
+// argument; bounded (cleared when full); thread-safe.
+namespace {
+struct MapKey {
+  uint64_t v[16];
+  bool operator==(const MapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (uint64_t x : k.v) {
+      h ^= x;
+      h *= 1099511628211ull;
+    }
+    return static_cast<size_t>(h);
+  }
+};
+std::mutex g_map_mu;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+constexpr size_t kMapCacheMax = 8192;
+}  // namespace
+
+static int encode_map_uncached(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank,
+                               const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
+
 static int encode_map_any(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank, const uint64_t* dims,
                           const uint64_t* strides_bytes, const uint32_t* box) {
+  if (rank < 1 || rank > 5) return set_err(FGT_ERR_ARG, "tensor map: rank=%d", rank);
+  MapKey key;
+  memset(&key, 0, sizeof(key));
+  key.v[0] = reinterpret_cast<uint64_t>(base);
+  key.v[1] = (static_cast<uint64_t>(dtype) << 8) | static_cast<uint64_t>(rank);
+  for (int i = 0; i < rank; ++i) key.v[2 + i] = dims[i];
+  for (int i = 0; i < rank - 1; ++i) key.v[7 + i] = strides_bytes[i];
+  for (int i = 0; i < rank; ++i) key.v[11 + i] = box[i];
+  {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    auto it = g_map_cache.find(key);
+    if (it != g_map_cache.end()) {
+      *out = it->second;
+      return FGT_OK;
+    }
+  }
+  const int rc = encode_map_uncached(out, dtype, base, rank, dims, strides_bytes, box);
+  if (rc == FGT_OK) {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    if (g_map_cache.size() >= kMapCacheMax) g_map_cache.clear();
+    g_map_cache.emplace(key, *out);
+  }
+  return rc;
+}
+
+static int encode_map_uncached(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank,
+                               const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_err(FGT_ERR_DEVICE, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   cuuint64_t gdim[5];

@@ -223,13 +223,21 @@ class FGT(nn.Module):
                     nn.init.constant_(m.bias.data, 0.0)
 
     # ------------------------------------------------------------------ weight packing (one-time)
+    def _drop_graphs(self):
+        """Captured CUDA graphs bake in the addresses of the packed weights and workspaces: whenever those are
+        re-created (new weights, .to(), .float() ...) the captures must go too, or a replay reads freed memory."""
+        if getattr(self, "_graphed", None) is not None:
+            self._graphed.entries.clear()
+
     def _apply(self, fn, *a, **k):
         self._packed = None
         self._geo = {}
+        self._drop_graphs()
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, *a, **k):
         self._packed = None
+        self._drop_graphs()
         return super().load_state_dict(*a, **k)
 
     def _perm_hidden(self, c):

@@ -118,6 +118,15 @@ def load():
     lib.fgt_tapsum.argtypes = [_c_p, ci, ci, ci, ci, ci, ci, ci, ci, cll, _c_p, ci, _c_p, cll, cll, cll, cll, _c_p]
     lib.fgt_tapsum.restype = ctypes.c_int
     lib.fgt_dwpool.argtypes = [_c_p, ci, _c_p, ci, ci, ci, ci, ci, ci, ci, _c_p, _c_p, _c_p, _c_p]
+    lib.fgt_binary_dilate.argtypes = [_c_p, ci, ci, ci, ci, _c_p, _c_p, _c_p]
+    lib.fgt_fill_holes_init.argtypes = [_c_p, ci, ci, ci, _c_p, _c_p]
+    lib.fgt_fill_holes_pass.argtypes = [_c_p, ci, ci, ci, _c_p, _c_p, ci, _c_p]
+    lib.fgt_fill_holes_finish.argtypes = [_c_p, ci, ci, ci, _c_p, _c_p]
+    lib.fgt_resize_nearest_u8.argtypes = [_c_p, ci, ci, ci, ci, ci, ci, _c_p, _c_p]
+    lib.fgt_resize_bilinear_f32.argtypes = [_c_p, ci, ci, ci, ci, ci, ci, ci, cf, cf, _c_p, _c_p]
+    for fn in (lib.fgt_binary_dilate, lib.fgt_fill_holes_init, lib.fgt_fill_holes_pass, lib.fgt_fill_holes_finish,
+               lib.fgt_resize_nearest_u8, lib.fgt_resize_bilinear_f32):
+        fn.restype = ctypes.c_int
     lib.fgt_conv_tail.argtypes = [_c_p, cll, ci, ci, ci, ci, _c_p, cll, ci, ci, _c_p, ci, _c_p, cll, cll, cll, cll, _c_p]
     lib.fgt_conv_tail.restype = ctypes.c_int
     lib.fgt_swin_prep.argtypes = [_c_p, _c_p, ci, ci, ci, ci, ci, _c_p, ci, ci, ci, ci, ci, _c_p, _c_p, _c_p, _c_p, _c_p,

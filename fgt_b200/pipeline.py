@@ -122,6 +122,10 @@ def compute_flows(backend, video_flow, args, mode):
     a, b = (video_flow[:-1], video_flow[1:]) if mode == "forward" else (video_flow[1:], video_flow[:-1])
     flows = backend.raft_pairs(a, b, args.raft_iters)                   # [N-1,2,h,w]
     out = np.empty((args.imgH, args.imgW, 2, flows.shape[0]), dtype=np.float32)   # (the driver grows it by concatenation)
+    if hasattr(backend, "resize_flows") and flows.shape[0] and tuple(flows.shape[2:]) != (args.imgH, args.imgW):
+        # device kernel for cv2.resize(INTER_LINEAR) + the rescaling of the flow vectors, all pairs in one batch
+        out[...] = np.moveaxis(backend.resize_flows(flows, args.imgH, args.imgW), 0, -1)
+        return out
     for i in range(flows.shape[0]):
         flow = np.ascontiguousarray(flows[i].transpose(1, 2, 0))
         h, w = flow.shape[:2]
@@ -133,8 +137,18 @@ def compute_flows(backend, video_flow, args, mode):
     return out
 
 
-def prepare_masks(masks_u8, args):
-    """:539-567 — per-frame uint8 masks [N,h,w] (non-zero = hole) -> (mask, mask_dilated, flow_mask) bool [H,W,N]."""
+def prepare_masks(masks_u8, args, backend=None):
+    """:539-567 — per-frame uint8 masks [N,h,w] (non-zero = hole) -> (mask, mask_dilated, flow_mask) bool [H,W,N].
+    A backend with `dilate_masks` (the GPU backend) runs the resize + both dilations of all frames as batched device
+    kernels (bit-identical to cv2.resize INTER_NEAREST / scipy.ndimage.binary_dilation)."""
+    if backend is not None and hasattr(backend, "dilate_masks") and len(masks_u8) and \
+            all(np.asarray(m).ndim == 2 and np.asarray(m).shape == np.asarray(masks_u8[0]).shape for m in masks_u8):
+        m0 = backend.resize_masks(np.stack([np.asarray(m).astype(np.uint8) for m in masks_u8], 0), args.imgH, args.imgW)
+        fm = backend.dilate_masks(m0, args.flow_mask_dilates) if args.flow_mask_dilates > 0 else m0
+        mk = backend.dilate_masks(m0, args.frame_dilates) if args.frame_dilates > 0 else m0
+        st = lambda a: np.moveaxis(np.ascontiguousarray(a).astype(bool), 0, -1)
+        # (without dilation the driver keeps the resized uint8 values; every consumer only tests them for non-zero)
+        return st(mk), st(np.stack([gradient_mask(x) for x in mk.astype(bool)], 0)), st(fm)
     mask, dilated, flow_mask = [], [], []
     for m in masks_u8:
         m = np.asarray(m)
@@ -195,7 +209,10 @@ def blend_frames(backend, video, gx, gy, mask, mask_gradient):
     def fill(i):
         mask_gradient[:, :, i] = scipy.ndimage.binary_fill_holes(mask_gradient[:, :, i]).astype(bool)
 
-    _per_frame(fill, N)
+    if hasattr(backend, "fill_holes"):                   # batched device kernel, bit-identical to scipy's
+        mask_gradient[...] = np.moveaxis(backend.fill_holes(np.moveaxis(mask_gradient, -1, 0)), 0, -1)
+    else:
+        _per_frame(fill, N)
     todo = [i for i in range(N) if mask[:, :, i].sum() > 0]
 
     def solve(ids):
@@ -259,6 +276,27 @@ class GpuBackend:
         from .regionfill import diffusion
         return diffusion(flows, masks)
 
+    # ---- the driver's mask / resize glue as device kernels (fgt_b200/morph.py): numpy in, numpy out
+    def resize_masks(self, masks, H, W):
+        from . import morph
+        return masks if tuple(masks.shape[1:]) == (H, W) else morph.resize_nearest(masks, (H, W), device=self.dev).cpu().numpy()
+
+    def dilate_masks(self, masks, iterations):
+        from . import morph
+        return morph.binary_dilation(masks, iterations, device=self.dev).cpu().numpy()
+
+    def fill_holes(self, masks):
+        from . import morph
+        return morph.binary_fill_holes(masks, device=self.dev).cpu().numpy()
+
+    def resize_flows(self, flows, H, W):
+        """[n,2,h,w] RAFT flows -> [n,H,W,2] at the working resolution, vectors rescaled (:264-268)."""
+        from . import morph
+        n, _, h, w = flows.shape
+        x = torch.as_tensor(flows).to(self.dev).permute(0, 2, 3, 1).contiguous()
+        return morph.resize_bilinear(x, (H, W), channel_scale=(float(W) / float(w), float(H) / float(h)),
+                                     device=self.dev).cpu().numpy()
+
     def lafc_complete(self, flows, masks, diffused, triplets, pivot):
         fl, mk, df = (torch.from_numpy(a).to(self.dev).unsqueeze(0) for a in (flows, masks, diffused))   # [1,c,t,H,W]
         out = []
@@ -320,6 +358,12 @@ class ShardedBackend:
         nccl = dist.get_backend(group) == "nccl"
         self.comm_dev = torch.device("cuda", torch.cuda.current_device()) if nccl else torch.device("cpu")
 
+    def __getattr__(self, name):
+        # the mask / resize glue kernels are cheap and run replicated on every rank: delegate when the inner backend has them
+        if name in ("resize_masks", "dilate_masks", "fill_holes", "resize_flows") and hasattr(self.inner, name):
+            return getattr(self.inner, name)
+        raise AttributeError(name)
+
     def _mine(self, n, costs=None):
         from .parallel import shard_items
         return shard_items(n, self.rank, self.world, costs)
@@ -331,6 +375,8 @@ class ShardedBackend:
         owners = [shard_items(n, r, self.world, costs) for r in range(self.world)]
         kmax = max(len(o) for o in owners)
         local = np.ascontiguousarray(local)
+        if n == 0 or kmax == 0:                          # nothing to exchange (e.g. a one-frame clip has no RAFT pairs)
+            return np.zeros((0,) + local.shape[1:], dtype=local.dtype)
         pad = np.zeros((kmax,) + local.shape[1:], dtype=local.dtype)
         pad[:local.shape[0]] = local
         t = torch.from_numpy(pad.view(np.uint8).reshape(kmax, -1)).to(self.comm_dev)
@@ -369,6 +415,8 @@ class ShardedBackend:
 
     def poisson_frames(self, trg, gx, gy, hole, gmask):
         n = len(trg)
+        if n == 0:
+            return []
         mine = self._mine(n)
         pick = lambda xs: [xs[i] for i in mine]
         res = self.inner.poisson_frames(pick(trg), pick(gx), pick(gy), pick(hole), pick(gmask)) if mine else []
@@ -443,7 +491,7 @@ def video_inpainting(frames_u8, masks_u8, backend, args=None, num_flows=3, flow_
         tile = lambda m: np.moveaxis(np.repeat(m[None], N, 0), 0, -1)           # the same mask for every frame (:531-535)
         mask, mask_dilated, flow_mask = tile(fm2), tile(md2), tile(fm2)
     else:
-        mask, mask_dilated, flow_mask = prepare_masks(masks_u8, args)
+        mask, mask_dilated, flow_mask = prepare_masks(masks_u8, args, backend)
     done_f = complete_flows(backend, flow_f, flow_mask, "forward", num_flows, flow_interval)
     done_b = complete_flows(backend, flow_b, flow_mask, "backward", num_flows, flow_interval)
     gx, gy = prepare_gradients(video, mask, mask_dilated)
@@ -486,7 +534,8 @@ def load_models(raft_model, lafc_ckpts, fgt_ckpts, device):
     fgt_sd, fgt_cfg = ckpt_dir(fgt_ckpts)
     fgt = FGTModel(fgt_cfg)
     fgt.load_state_dict(fgt_sd)
-    return GpuBackend(raft, lafc.to(device), fgt.to(device), device=device), lafc_cfg
+    # inference only: no BatchNorm / dropout in LAFC or FGT (the driver never calls .eval() on them), but be explicit
+    return GpuBackend(raft, lafc.to(device).eval(), fgt.to(device).eval(), device=device), lafc_cfg
 
 
 def main(argv=None):

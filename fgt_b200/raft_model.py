@@ -99,13 +99,20 @@ class RAFT(nn.Module):
         self._packed = None
         self._bufs = {}
 
+    def _drop_graphs(self):
+        """Captured CUDA graphs hold the addresses of the packed weights / workspaces they were recorded with."""
+        if getattr(self, "_graphs", None) is not None:
+            self._graphs.clear()
+
     def _apply(self, fn, *a, **k):
         self._packed = None
         self._bufs = {}
+        self._drop_graphs()
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, *a, **k):
         self._packed = None
+        self._drop_graphs()
         return super().load_state_dict(*a, **k)
 
     # ------------------------------------------------------------------ weight packing

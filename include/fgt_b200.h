@@ -316,6 +316,31 @@ int fgt_tapsum(const float* y, int n, int H, int W, int cout, int kx, int ky, in
 int fgt_dwpool(const float* a, int ca, const float* b, int cb, int bt, int h, int w, int k, int gh, int gw,
                const float* weight, const float* bias, float* out, fgt_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Mask / resize glue of the driver on the device (tool/video_inpainting.py:264-268,546-561,637).
+ * Masks are uint8 [B,H,W] (0 / non-zero); every call is bit-exact against the library call it replaces.
+ *   fgt_binary_dilate     scipy.ndimage.binary_dilation(m, iterations=n): n passes of the 3x3 cross, border 0;
+ *                         `tmp` is a second [B,H,W] scratch buffer, the result lands in `out`.
+ *   fgt_fill_holes_*      scipy.ndimage.binary_fill_holes(m): init zeroes `reach`; each pass propagates "background
+ *                         connected to the border" along whole rows and columns and sets *changed (device int) when
+ *                         anything moved — the caller repeats until it stays 0; finish writes out = !reach.
+ *   fgt_resize_nearest_u8 cv2.resize(..., INTER_NEAREST) on [B,H,W,C] uint8.
+ *   fgt_resize_bilinear_f32  cv2.resize(..., INTER_LINEAR) on float32 [B,H,W,C] (nchw = 0) — optionally scaling channel
+ *                         0 / 1 of the result (the driver rescales resized flow vectors, :266-267) — or
+ *                         F.interpolate(mode="bilinear", align_corners=False) on [B,C,H,W] (nchw = 1); agrees with the
+ *                         libraries to float32 rounding of the two 1-D interpolations.
+ * ------------------------------------------------------------------------------------------ */
+int fgt_binary_dilate(const unsigned char* in, int B, int H, int W, int iterations, unsigned char* tmp, unsigned char* out,
+                      fgt_stream_t stream);
+int fgt_fill_holes_init(const unsigned char* fg, int B, int H, int W, unsigned char* reach, fgt_stream_t stream);
+int fgt_fill_holes_pass(const unsigned char* fg, int B, int H, int W, unsigned char* reach, int* changed, int passes,
+                        fgt_stream_t stream);
+int fgt_fill_holes_finish(const unsigned char* reach, int B, int H, int W, unsigned char* out, fgt_stream_t stream);
+int fgt_resize_nearest_u8(const unsigned char* in, int B, int H, int W, int C, int OH, int OW, unsigned char* out,
+                          fgt_stream_t stream);
+int fgt_resize_bilinear_f32(const float* in, int B, int H, int W, int C, int OH, int OW, int nchw, float scale_c0,
+                            float scale_c1, float* out, fgt_stream_t stream);
+
 /* 3x3 convolution (zero padding 1, stride 1) with cout <= 3 output channels + bias + activation in one kernel: the
  * nine taps become the N dimension of a tcgen05 GEMM over the input positions (activation read once) and are summed
  * per output pixel in shared memory — the decoder's final conv + tanh (FGT/models/model.py:185-193). x: NHWC

@@ -132,7 +132,8 @@ def test_linear_rowmap_and_transposed_store():
     assert_close(got, ref, KTOL, "transposed store")
 
 
-@pytest.mark.parametrize("batches,heads,L,qs", [(1, 1, 64, 1.0), (1, 2, 200, 1.0), (2, 4, 1800, 3.0), (4, 4, 37, 1.0)])
+@pytest.mark.parametrize("batches,heads,L,qs", [(1, 1, 64, 1.0), (1, 2, 200, 1.0), (2, 4, 1800, 3.0), (4, 4, 37, 1.0),
+                                                (1, 1, 21060, 2.0)])  # last: one 720p zone at T=13 (BASELINE config 5)
 def test_attention_dense(batches, heads, L, qs):
     from tools import diag_attn as D
     assert D.dense_case(batches, heads, L, qscale=qs)
