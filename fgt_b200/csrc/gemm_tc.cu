@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
       }
 
       // stage this tile's bias slice (zeros beyond N / without bias); 128 epilogue threads cooperate
-      float* sbias = sbias_base + (lt & 1) * 256;
+      float* sbias = sbias_base + (lt & 1) * p.bn;  // two bn-float slices (sized exactly: 3 stages + staging must fit)
       for (int c = threadIdx.x - 64; c < p.bn; c += 128)
         sbias[c] = (p.bias && n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.f;
       asm volatile("bar.sync 1, 128;\n" ::: "memory");
@@ -798,7 +798,9 @@ int gemm_tc_launch(const FgtGemmDesc& d, cudaStream_t stream) {
   // More slots let the stores of one chunk drain while the next is written — what short-K layers need; long-K
   // layers keep the shared memory for pipeline stages instead.
   p.stg_slot_bytes = static_cast<int>(p.out_half ? kAPlaneBytes : 2 * kAPlaneBytes);
-  const uint32_t base_fixed = 1024u /*align*/ + 256u /*barriers*/ + 2048u /*bias*/;
+  // alignment slack + barriers + two bias slices of bn floats. Sized exactly: a 128-wide split-bf16 tile with the
+  // TMA epilogue needs 3 x 64 KB stages + 32 KB of panels + this block within the 227 KB limit.
+  const uint32_t base_fixed = 1024u /*align*/ + 256u /*barriers*/ + 2u * static_cast<uint32_t>(d.bn) * 4u /*bias*/;
   int stages = 0;
   p.stg_slots = 0;
   if (p.tma_out) {

@@ -63,50 +63,56 @@ __global__ void im2col_nchw_kernel(const float* __restrict__ s0, int c0, const f
                                    long long plane) {
   pdl_launch_dependents();
   pdl_wait();
-  // one block = one output row (b, oy); threadIdx.x = 8-channel group, threadIdx.y strides over ox.
-  // The channel -> (source channel, dy, dx) decode is a per-block shared-memory table: no per-element
-  // integer divisions in the loop (they dominated the first version of this kernel).
-  __shared__ short tab_c[256], tab_dy[256], tab_dx[256];
+  // one block = one output row (b, oy). The k input rows the row needs (all cin channels, padded to the width the
+  // taps reach: Wp = (OW-1)*stride + k) are staged in shared memory first — coalesced global reads, bounds /
+  // replication handled once per staged element — so the gather itself is 8 shared-memory loads per 16-byte store.
+  extern __shared__ float srow[];  // [k][cin][Wp]
   const int cin = c0 + c1;
-  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  for (int ch = tid; ch < cpad; ch += blockDim.x * blockDim.y) {
-    if (ch < k * k * cin) {
-      const int tap = ch / cin;
-      tab_c[ch] = static_cast<short>(ch - tap * cin);
-      tab_dy[ch] = static_cast<short>(tap / k - pad);
-      tab_dx[ch] = static_cast<short>(tap % k - pad);
+  const int Wp = (OW - 1) * stride + k;
+  const int b = blockIdx.x / OH, oy = blockIdx.x - b * OH;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+  const long long HWl = static_cast<long long>(H) * W;
+  const int row_elems = cin * Wp;
+  for (int idx = tid; idx < k * row_elems; idx += nthr) {
+    const int ky = idx / row_elems;
+    const int r = idx - ky * row_elems;
+    const int c = r / Wp;
+    const int xx = r - c * Wp;
+    int y = oy * stride + ky - pad, x = xx - pad;
+    bool ok = true;
+    if (replicate) {
+      y = min(max(y, 0), H - 1);
+      x = min(max(x, 0), W - 1);
     } else {
-      tab_c[ch] = -1;
-      tab_dy[ch] = tab_dx[ch] = 0;
+      ok = y >= 0 && y < H && x >= 0 && x < W;
+    }
+    float v = 0.f;
+    if (ok)
+      v = fmaf((c < c0) ? __ldg(s0 + (static_cast<long long>(b) * c0 + c) * HWl + static_cast<long long>(y) * W + x)
+                        : __ldg(s1 + (static_cast<long long>(b) * c1 + (c - c0)) * HWl + static_cast<long long>(y) * W + x),
+               scale, shift);
+    srow[idx] = v;
+  }
+  // this thread's 8 output channels: ch = (ky*k + kx)*cin + c  ->  offset of (ky, c, kx) in the staged rows
+  const int g = threadIdx.x;
+  int off[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = g * 8 + j;
+    if (ch < k * k * cin) {
+      const int tap = ch / cin, c = ch - tap * cin;
+      const int ky = tap / k, kx = tap - ky * k;
+      off[j] = (ky * cin + c) * Wp + kx;
+    } else {
+      off[j] = -1;
     }
   }
   __syncthreads();
-  const int b = blockIdx.x / OH, oy = blockIdx.x - b * OH;
-  const int g = threadIdx.x;
-  const long long HWl = static_cast<long long>(H) * W;
   for (int ox = threadIdx.y; ox < OW; ox += blockDim.y) {
+    const int x0 = ox * stride;
     float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int ch = g * 8 + j;
-      const int c = tab_c[ch];
-      float val = 0.f;
-      if (c >= 0) {
-        int y = oy * stride + tab_dy[ch], x = ox * stride + tab_dx[ch];
-        bool ok = true;
-        if (replicate) {
-          y = min(max(y, 0), H - 1);
-          x = min(max(x, 0), W - 1);
-        } else {
-          ok = y >= 0 && y < H && x >= 0 && x < W;
-        }
-        if (ok)
-          val = fmaf((c < c0) ? __ldg(s0 + (static_cast<long long>(b) * c0 + c) * HWl + y * W + x)
-                              : __ldg(s1 + (static_cast<long long>(b) * c1 + (c - c0)) * HWl + y * W + x),
-                     scale, shift);
-      }
-      v[j] = val;
-    }
+    for (int j = 0; j < 8; ++j) v[j] = off[j] >= 0 ? srow[off[j] + x0] : 0.f;
     const long long o = ((static_cast<long long>(b) * OH + oy) * OW + ox) * cpad + g * 8;
     if (plane == 0) {  // single-plane fp16 rows (input of a 1-term layer)
       *reinterpret_cast<uint4*>(hi + o) = make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]),
@@ -372,6 +378,69 @@ __global__ void unfold_kernel(const float* __restrict__ img, int bt, int th, int
   }
 }
 
+// fold -> (divide by coverage) -> unfold -> ReLU of the fusion FFN (ffn_base.py:57-75) WITHOUT the image round trip:
+// every entry of a token's hidden patch belongs to exactly one pixel of the folded feature map, and the unfolded value
+// at that entry is the (normalised) sum over all entries that map to the same pixel. One block = one image row (b, y):
+// for each pixel the <= 9 covering (token, patch position) entries are summed in the same order as fold_kernel
+// (bit-identical to fgt_fold + fgt_unfold), scaled, rectified, split once and written back to those same entries.
+// Pixels that no patch covers do not exist for kernel >= stride; entries whose pixel lies in the padding ring are
+// zeros (nn.Unfold pads with zeros) and are written by the second loop.
+__global__ void fold_unfold_kernel(const float* __restrict__ hid, int bt, int th, int tw, int C, int kh, int kw, int st,
+                                   int pd, int OH, int OW, int relu, __nv_bfloat16* __restrict__ hi, long long plane) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int C4 = C / 4;
+  if (threadIdx.x >= C4) return;
+  const int hidden = kh * kw * C;
+  const int c = threadIdx.x * 4;
+  // rows y in [-pd, OH + pd): the padded rows only produce zeros
+  const int HP = OH + 2 * pd;
+  const int b = blockIdx.x / HP, y = blockIdx.x - b * HP - pd;
+  const bool y_in = y >= 0 && y < OH;
+  const int ty_hi = min((y + pd) / st, th - 1);
+  for (int x = static_cast<int>(threadIdx.y) - pd; x < OW + pd; x += blockDim.y) {
+    const bool in = y_in && x >= 0 && x < OW;
+    const int tx_hi = min((x + pd) / st, tw - 1);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cnt = 0;
+    if (in) {
+      for (int ty = ty_hi; ty >= 0; --ty) {
+        const int ky = y + pd - st * ty;
+        if (ky >= kh) break;
+        for (int tx = tx_hi; tx >= 0; --tx) {
+          const int kx = x + pd - st * tx;
+          if (kx >= kw) break;
+          const float4 v = __ldg(reinterpret_cast<const float4*>(
+              hid + ((static_cast<long long>(b) * th + ty) * tw + tx) * hidden + (ky * kw + kx) * C + c));
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+          ++cnt;
+        }
+      }
+      const float sc = 1.f / static_cast<float>(cnt);
+      acc.x *= sc; acc.y *= sc; acc.z *= sc; acc.w *= sc;
+      if (relu) {
+        acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+      }
+    }
+    uint32_t h0, l0, h1, l1;
+    split_bf16x2(acc.x, acc.y, h0, l0);
+    split_bf16x2(acc.z, acc.w, h1, l1);
+    for (int ty = ty_hi; ty >= 0; --ty) {
+      const int ky = y + pd - st * ty;
+      if (ky >= kh) break;
+      if (ky < 0) continue;
+      for (int tx = tx_hi; tx >= 0; --tx) {
+        const int kx = x + pd - st * tx;
+        if (kx >= kw) break;
+        if (kx < 0) continue;
+        const long long o = ((static_cast<long long>(b) * th + ty) * tw + tx) * hidden + (ky * kw + kx) * C + c;
+        *reinterpret_cast<uint2*>(hi + o) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(hi + plane + o) = make_uint2(l0, l1);
+      }
+    }
+  }
+}
+
 // nearest x2 upsampling of an NHWC split tensor (F.interpolate(scale_factor=2), network_blocks_2d.py:58-60)
 __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ in, long long in_plane, int n, int H, int W,
                                   int C, __nv_bfloat16* __restrict__ out, long long out_plane) {
@@ -475,7 +544,15 @@ extern "C" int fgt_im2col_nchw(const float* src0, int c0, const float* src1, int
               FGT_ERR_ARG, "im2col_nchw: k=%d cin=%d cpad=%d", k, c0 + c1, cpad);
   FGT_REQUIRE(cpad <= 256, FGT_ERR_ARG, "im2col_nchw: cpad=%d > 256", cpad);
   const dim3 blk(cpad / 8, 256 / (cpad / 8));
-  launch_k(im2col_nchw_kernel, dim3(n * OH), dim3(blk), 0, reinterpret_cast<cudaStream_t>(stream), 
+  const size_t smem = static_cast<size_t>(k) * (c0 + c1) * ((OW - 1) * stride + k) * sizeof(float);
+  constexpr size_t kIm2colSmemMax = 160 * 1024;
+  FGT_REQUIRE(smem <= kIm2colSmemMax, FGT_ERR_ARG, "im2col_nchw: %zu bytes of staged input rows exceed %zu", smem, kIm2colSmemMax);
+  static bool attr_set = false;
+  if (!attr_set) {
+    FGT_CUDA(cudaFuncSetAttribute(im2col_nchw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kIm2colSmemMax)));
+    attr_set = true;
+  }
+  launch_k(im2col_nchw_kernel, dim3(n * OH), dim3(blk), smem, reinterpret_cast<cudaStream_t>(stream), 
       src0, c0, src1, c1, n, H, W, k, stride, pad, replicate, OH, OW, cpad, scale, shift,
       reinterpret_cast<__nv_bfloat16*>(out_hi), out_plane);
   FGT_CUDA(cudaGetLastError());
@@ -557,6 +634,20 @@ extern "C" int fgt_unfold(const float* img, int bt, int th, int tw, int C, int k
   const dim3 blk(gx, 256 / gx);
   launch_k(unfold_kernel, dim3(bt * th * tw), dim3(blk), 0, reinterpret_cast<cudaStream_t>(stream), 
       img, bt, th, tw, C, kh, kw, stride, pad, OH, OW, relu, reinterpret_cast<__nv_bfloat16*>(out_hi), out_plane);
+  FGT_CUDA(cudaGetLastError());
+  return FGT_OK;
+}
+
+extern "C" int fgt_fold_unfold(const float* hid, int bt, int th, int tw, int C, int kh, int kw, int stride, int pad,
+                               int OH, int OW, int relu, void* out_hi, long long out_plane, fgt_stream_t stream) {
+  FGT_REQUIRE(hid && out_hi && C % 4 == 0 && C / 4 <= 64, FGT_ERR_ARG, "fold_unfold: C=%d", C);
+  FGT_REQUIRE(kh >= stride && kw >= stride, FGT_ERR_ARG, "fold_unfold: kernel %dx%d must cover the stride %d", kh, kw, stride);
+  FGT_REQUIRE((th - 1) * stride + kh - 2 * pad >= OH && (tw - 1) * stride + kw - 2 * pad >= OW, FGT_ERR_ARG,
+              "fold_unfold: patches do not cover the %dx%d map", OH, OW);
+  const int gx = (C / 4 + 1) / 2 * 2;
+  const dim3 blk(gx, 256 / gx);
+  launch_k(fold_unfold_kernel, dim3(bt * (OH + 2 * pad)), dim3(blk), 0, reinterpret_cast<cudaStream_t>(stream), hid, bt, th, tw, C, kh,
+           kw, stride, pad, OH, OW, relu, reinterpret_cast<__nv_bfloat16*>(out_hi), out_plane);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;
 }

@@ -456,12 +456,11 @@ class FGT(nn.Module):
         hidden = k * k * self.mlp_c
         y = self._buf(g, "ffn_y", (rows, d), dev, split=True)
         hid = self._buf(g, "ffn_hid", (rows, hidden), dev)
-        img = self._buf(g, "ffn_img", (g.bt, g.OH, g.OW, self.mlp_c), dev)
         hid2 = self._buf(g, "ffn_hid2", (rows, hidden), dev, split=True)
         lib.rownorm(x, None, y, rows_per_batch=rows, total_rows=rows, dst_batch_rows=rows, eps=LN_EPS)
         self._linear([lib.ASeg(y, d, rows)], P[name + ".ffn1"], rows, out_f32=hid)
-        lib.fold(hid, g.bt, g.h, g.w, self.mlp_c, k, k, s, p, g.OH, g.OW, normalize=True, out=img)
-        lib.unfold(img, g.bt, g.h, g.w, self.mlp_c, k, k, s, p, g.OH, g.OW, hid2, relu=True)
+        # fold / coverage division / unfold / ReLU (ffn_base.py:57-75) in one launch, no image round trip
+        lib.fold_unfold(hid, g.bt, g.h, g.w, self.mlp_c, k, k, s, p, g.OH, g.OW, hid2, relu=True)
         self._linear([lib.ASeg(hid2, hidden, rows)], P[name + ".ffn2"], rows, aux=x, aux_mode=lib.AUX_ADD, out_f32=x,
                      out_split=xs)
 

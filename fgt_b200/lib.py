@@ -135,6 +135,8 @@ def load():
     lib.fgt_dwconv3x3_res.argtypes = [_c_p, ci, ci, ci, ci, _c_p, _c_p, _c_p, _c_p, cll, _c_p]
     lib.fgt_fold.argtypes = [_c_p, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, _c_p, _c_p, _c_p, cll, _c_p]
     lib.fgt_unfold.argtypes = [_c_p, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, _c_p, cll, _c_p]
+    lib.fgt_fold_unfold.argtypes = [_c_p, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, _c_p, cll, _c_p]
+    lib.fgt_fold_unfold.restype = ctypes.c_int
     lib.fgt_upsample2x.argtypes = [_c_p, cll, ci, ci, ci, ci, _c_p, cll, _c_p]
     for fn in (lib.fgt_pack_nchw, lib.fgt_rownorm, lib.fgt_dwpool, lib.fgt_dwconv3x3_res, lib.fgt_fold,
                lib.fgt_unfold, lib.fgt_upsample2x):
@@ -474,6 +476,13 @@ def unfold(img, bt, th, tw, C, kh, kw, stride, pad, OH, OW, out_split, relu=True
     with _Prof("unfold", tag, 0, 4.0 * bt * (th * tw * kh * kw * C + OH * OW * C)):
         check(load().fgt_unfold(_dp(img), bt, th, tw, C, kh, kw, stride, pad, OH, OW, 1 if relu else 0,
                                 _dp(out_split), plane_elems(out_split), stream_ptr()), "fgt_unfold")
+
+
+def fold_unfold(hid, bt, th, tw, C, kh, kw, stride, pad, OH, OW, out_split, relu=True, tag=""):
+    """fold (normalised) + unfold (+ReLU) of the fusion FFN in one launch: hid fp32 [bt*th*tw, kh*kw*C] -> split."""
+    with _Prof("fold_unfold", tag, 0, 8.0 * bt * th * tw * kh * kw * C):
+        check(load().fgt_fold_unfold(_dp(hid), bt, th, tw, C, kh, kw, stride, pad, OH, OW, 1 if relu else 0,
+                                     _dp(out_split), plane_elems(out_split), stream_ptr()), "fgt_fold_unfold")
 
 
 def upsample2x(in_split, n, H, W, C, out_split, tag=""):

@@ -374,6 +374,13 @@ int fgt_dwconv3x3_res(const float* x, int bt, int h, int w, int C, const float* 
 int fgt_fold(const float* hid, int bt, int th, int tw, int C, int kh, int kw, int stride, int pad, int OH, int OW,
              int normalize, const float* add, float* out, void* out_hi, long long out_plane, fgt_stream_t stream);
 
+/* fgt_fold(normalize = 1) followed by fgt_unfold(relu) in one launch, without the [bt,OH,OW,C] image round trip
+ * (FusionFeedForward's fold / coverage division / unfold / ReLU, ffn_base.py:57-75,40): every entry of the hidden
+ * patches becomes the rectified mean over the entries that fold onto the same pixel. hid fp32 [bt*th*tw, kh*kw*C]
+ * position-major -> split-bf16 of the same shape; bit-identical to the two-launch sequence. */
+int fgt_fold_unfold(const float* hid, int bt, int th, int tw, int C, int kh, int kw, int stride, int pad, int OH, int OW,
+                    int relu, void* out_hi, long long out_plane, fgt_stream_t stream);
+
 /* nn.Unfold (+ optional ReLU) of [bt,OH,OW,C] into position-major token patches (split). */
 int fgt_unfold(const float* img, int bt, int th, int tw, int C, int kh, int kw, int stride, int pad, int OH,
                int OW, int relu, void* out_hi, long long out_plane, fgt_stream_t stream);

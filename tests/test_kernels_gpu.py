@@ -329,3 +329,56 @@ def test_conv_tail_vs_torch(n, H, W, cin, cout, act):
     lib.conv_tail(xs, n, H, W, cin, ws, cout, b, act, out2, nchw=False)
     torch.cuda.synchronize()
     assert_close(out2.permute(0, 3, 1, 2), ref, KTOL, "conv_tail nhwc")
+
+
+@pytest.mark.parametrize("c0,c1,k,stride,pad,replicate,half", [(3, 1, 3, 2, 1, False, False), (2, 0, 5, 1, 2, True, True),
+                                                               (3, 0, 7, 2, 3, False, False)])
+def test_im2col_nchw_vs_torch(c0, c1, k, stride, pad, replicate, half):
+    """fgt_im2col_nchw (rows of k*k*cin gathered inputs, (ky,kx)-major / channel-minor, zero or replication padding,
+    optional affine on in-bounds samples, split-bf16 or fp16 rows) against F.unfold on the padded input."""
+    lib = _lib()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(6)
+    n, H, W = 2, 37, 52
+    a = torch.randn(n, c0, H, W, device=dev)
+    b = torch.randn(n, c1, H, W, device=dev) if c1 else None
+    x = torch.cat([a, b], 1) if c1 else a
+    cin = c0 + c1
+    OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    cpad = (k * k * cin + 63) // 64 * 64
+    scale, shift = (2.0 / 255.0, -1.0) if k == 7 else (1.0, 0.0)
+    out = (torch.full((n, OH, OW, cpad), 9.0, dtype=torch.float16, device=dev) if half
+           else torch.full((2, n, OH, OW, cpad), 9.0, dtype=torch.bfloat16, device=dev))
+    lib.im2col_nchw(a, b, out, k=k, stride=stride, pad=pad, replicate=replicate, OH=OH, OW=OW, scale=scale, shift=shift)
+    torch.cuda.synchronize()
+    xa = x.double() * scale + shift
+    xp = F.pad(xa, (pad,) * 4, mode="replicate") if replicate else F.pad(xa, (pad,) * 4)
+    cols = F.unfold(xp, k, stride=stride).reshape(n, cin, k * k, OH, OW)           # [n, c, tap, oy, ox]
+    ref = cols.permute(0, 3, 4, 2, 1).reshape(n, OH, OW, k * k * cin)              # channel = tap*cin + c
+    got = out.float() if half else lib.from_split(out)
+    assert_close(got[..., :k * k * cin], ref, 1e-3 if half else KTOL, "im2col rows")
+    assert (got[..., k * k * cin:] == 0).all()
+
+
+@pytest.mark.parametrize("bt,th,tw,C", [(2, 20, 36, 40), (1, 22, 36, 40), (1, 5, 7, 8)])
+def test_fold_unfold_fused_equals_two_launches(bt, th, tw, C):
+    """fgt_fold_unfold == fgt_fold(normalize) -> fgt_unfold(relu), bit for bit (and both == nn.Fold / nn.Unfold, fp64)."""
+    lib = _lib()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(7)
+    k, s, p = 7, 3, 3
+    OH, OW = (th - 1) * s + k - 2 * p, (tw - 1) * s + k - 2 * p
+    hid = torch.randn(bt * th * tw, k * k * C, device=dev)
+    img = torch.empty(bt, OH, OW, C, device=dev)
+    two = torch.full((2, bt * th * tw, k * k * C), 3.0, dtype=torch.bfloat16, device=dev)
+    one = torch.full_like(two, 5.0)
+    lib.fold(hid, bt, th, tw, C, k, k, s, p, OH, OW, normalize=True, out=img)
+    lib.unfold(img, bt, th, tw, C, k, k, s, p, OH, OW, two, relu=True)
+    lib.fold_unfold(hid, bt, th, tw, C, k, k, s, p, OH, OW, one, relu=True)
+    torch.cuda.synchronize()
+    assert torch.equal(one, two)
+    # fp64 reference through nn.Fold / nn.Unfold (hidden index is position-major here: p*C + c)
+    cols = hid.double().reshape(bt, th * tw, k * k, C).permute(0, 3, 2, 1).reshape(bt, C * k * k, th * tw)
+    im = F.fold(cols, (OH, OW), k, stride=s, padding=p) / F.fold(torch.ones_like(cols), (OH, OW), k, stride=s, padding=p)
+    ref = F.relu(F.unfold(im, k, stride=s, padding=p)).reshape(bt, C, k * k, th * tw).permute(0, 3, 2, 1).reshape(bt * th * tw, -1)
+    assert_close(lib.from_split(one), ref, KTOL, "fold_unfold vs nn.Fold/nn.Unfold")

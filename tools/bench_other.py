@@ -172,7 +172,7 @@ def run(args, rank, local_rank, world, out):
         lafc = LAFC(synth.CFG_LAFC)
         lafc.load_state_dict(synth.make_state_dict(synth.lafc_param_shapes(), seed=5))
         lafc = lafc.to(dev)
-        lafc.enable_cuda_graph(True)
+        lafc.net.enable_cuda_graph(True)
         npairs = 2 * (T - 1)
         im1, im2 = synth.raft_inputs(seed=5 + rank, H=H, W=W, n=npairs)          # forward and backward pairs of the clip
         h1, h2 = im1.pin_memory(), im2.pin_memory()
@@ -205,7 +205,7 @@ def run(args, rank, local_rank, world, out):
         ms_e2e = parallel.max_over_ranks(_events(lambda: step(True), max(2, args.steps // 2), 2, flush, barrier), dev)
         clocks = sampler.stop()
         raft.enable_cuda_graph(False)
-        lafc.enable_cuda_graph(False)
+        lafc.net.enable_cuda_graph(False)
         with torch.no_grad():
             raft(d1[:rb], d2[:rb], iters=20, test_mode=True)
             lafc(dfl, dmk, None)
