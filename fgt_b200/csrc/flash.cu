@@ -51,6 +51,7 @@ struct FlashParams {
   __nv_bfloat16* out_hi;
   long long out_plane, out_batch_stride;
   int out_ld;
+  const int* out_rowmap;  // optional: query row (batch * Lq + row) -> output row of a [rows, out_ld] buffer, < 0 = dropped
   long long* trace;  // optional per-tile clock64 trace of CTA (0,0,0): [role 0..2][tile][8]
 };
 
@@ -344,14 +345,24 @@ __global__ void __launch_bounds__(256, 1) flash_kernel(const __grid_constant__ F
     mbar_wait(p_empty((n_tiles - 1) & 1), ((n_tiles - 1) >> 1) & 1u);
     tc_fence_after();
     const float inv = 1.f / l_run;
-    __nv_bfloat16* oh = p.out_hi + batch * p.out_batch_stride + static_cast<long long>(qrow) * p.out_ld + head * 128;
+    // Output row: in place (batch-strided), or scattered through the row map — the attention then undoes the zone /
+    // window regrouping itself (attention_base.py:100-103, attention_flow.py:165-168) and the output projection is a
+    // plain row-major GEMM over the real tokens only.
+    bool row_ok = qrow < p.Lq;
+    long long orow = batch * p.out_batch_stride + static_cast<long long>(qrow) * p.out_ld;
+    if (p.out_rowmap && row_ok) {
+      const int m = __ldg(p.out_rowmap + static_cast<long long>(batch) * p.Lq + qrow);
+      row_ok = m >= 0;
+      orow = static_cast<long long>(m) * p.out_ld;
+    }
+    __nv_bfloat16* oh = p.out_hi + orow + head * 128;
     __nv_bfloat16* ol = oh + p.out_plane;
 #pragma unroll
     for (int c0 = 0; c0 < 128; c0 += 32) {
       uint32_t raw[32];
       tmem_ld32(lane_base + kTmO + c0, raw);
       tmem_ld_wait();
-      if (qrow < p.Lq) {
+      if (row_ok) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint32_t hw[4], lw[4];
@@ -428,6 +439,7 @@ int attention_launch(const FgtAttnDesc& d, cudaStream_t stream) {
   p.out_plane = d.out_plane;
   p.out_batch_stride = d.out_batch_stride;
   p.out_ld = d.out_ld;
+  p.out_rowmap = d.out_rowmap;
   p.trace = g_flash_trace;
   FGT_REQUIRE((reinterpret_cast<uintptr_t>(d.out_hi) & 15) == 0, FGT_ERR_ARG, "attention: output misaligned");
 

@@ -642,7 +642,8 @@ extern "C" int fgt_fold_unfold(const float* hid, int bt, int th, int tw, int C, 
                                int OH, int OW, int relu, void* out_hi, long long out_plane, fgt_stream_t stream) {
   FGT_REQUIRE(hid && out_hi && C % 4 == 0 && C / 4 <= 64, FGT_ERR_ARG, "fold_unfold: C=%d", C);
   FGT_REQUIRE(kh >= stride && kw >= stride, FGT_ERR_ARG, "fold_unfold: kernel %dx%d must cover the stride %d", kh, kw, stride);
-  FGT_REQUIRE((th - 1) * stride + kh - 2 * pad >= OH && (tw - 1) * stride + kw - 2 * pad >= OW, FGT_ERR_ARG,
+  // every pixel of the map must lie under at least one patch (last patch ends at (th-1)*stride + kh - 1 - pad)
+  FGT_REQUIRE((th - 1) * stride + kh - pad >= OH && (tw - 1) * stride + kw - pad >= OW && pad < kh && pad < kw, FGT_ERR_ARG,
               "fold_unfold: patches do not cover the %dx%d map", OH, OW);
   const int gx = (C / 4 + 1) / 2 * 2;
   const dim3 blk(gx, 256 / gx);

@@ -266,7 +266,17 @@ class FGT(nn.Module):
                            b=sd[key + ".bias"].contiguous().to(dev), N=sd[key + ".weight"].shape[0], name=name)
         conv("enc10", enc + "10", [128, 192])
         conv("enc12", enc + "12", [64, 128])
-        conv("enc14", enc + "14", [32, 48])
+        # enc14 (8 groups of 32+48 -> 32 channels) as 2 super-groups of 4 with block-diagonal weights: the engine then
+        # works on 128-wide tiles and full 64-channel chunks (5 per tap for 4 groups instead of 2 half-empty ones per
+        # group), which cuts its operand traffic by 3/8 at the price of multiplying exact zeros
+        w14, G14 = sd[enc + "14.weight"], 4
+        co_g, c0_g, c1_g = w14.shape[0] // 8, 32, 48
+        wbd = torch.zeros(w14.shape[0], G14 * (c0_g + c1_g), 3, 3, dtype=w14.dtype, device=w14.device)
+        for gi in range(8):
+            j, rows_o = gi % G14, slice(gi * co_g, (gi + 1) * co_g)
+            wbd[rows_o, j * c0_g:(j + 1) * c0_g] = w14[rows_o, :c0_g]
+            wbd[rows_o, G14 * c0_g + j * c1_g:G14 * c0_g + (j + 1) * c1_g] = w14[rows_o, c0_g:]
+        put("enc14", wbd, sd[enc + "14.bias"], [G14 * c0_g, G14 * c1_g])
         conv("enc16", enc + "16", [256, 256])
         for name, key in (("fenc2", "flow_encoder.2.featureConv"), ("fenc3", "flow_encoder.3.featureConv"),
                           ("fenc4", "flow_encoder.4.featureConv"), ("f_patch2vec", "f_patch2vec")):
@@ -404,7 +414,7 @@ class FGT(nn.Module):
     # ------------------------------------------------------------------ op helpers
     @staticmethod
     def _conv(x, cin, n, h, w, wp, k, *, stride=1, pad=None, act=lib.ACT_LEAKY02, out_split=None, out_f32=None,
-              extra_seg=None, groups=1, seg_counts=None, nchw_out=False, terms=3, out_f16=None):
+              extra_seg=None, groups=1, seg_counts=None, nchw_out=False, terms=3, out_f16=None, alg_k=None):
         """NHWC split x [2,n,h,w,cin] (+ optional second segment) -> conv -> NHWC outputs."""
         pad = k // 2 if pad is None else pad
         oh = (h + 2 * pad - k) // stride + 1
@@ -424,7 +434,8 @@ class FGT(nn.Module):
             strides = dict(os_z=oh * ow * N, os_y=ow * N, os_x=N, os_c=1)
         lib.gemm_tc(segs, wp["w"], N, kx=k, ky=k, stride=stride, pad_x=pad, pad_y=pad, groups=groups, out_w=ow,
                     out_h=oh, out_z=n, box_w=bw, box_h=bh, bn=_pick_bn(N // groups, groups, wp["name"]), bias=wp["b"], act=act,
-                    out_f32=out_f32, out_split=out_split, out_f16=out_f16, tag=wp["name"], terms=terms, **strides)
+                    out_f32=out_f32, out_split=out_split, out_f16=out_f16, tag=wp["name"], terms=terms, alg_k=alg_k,
+                    **strides)
         return oh, ow
 
     @staticmethod
@@ -445,10 +456,13 @@ class FGT(nn.Module):
         lib.gemm_tc(segs, wp["w"], wp["N"], out_w=rows, bn=bn or _pick_bn(wp["N"], 1, wp["name"]), bias=wp["b"],
                     tag=wp["name"], **kw)
 
-    def _ffn(self, g, P, name, x, xs, dev):
-        """x += FusionFeedForward(LN(x)) (ffn_base.py:53-77, model.py:128-129 / 147-148)."""
+    def _ffn(self, g, P, name, x, xs, dev, need_split=True):
+        """x += FusionFeedForward(LN(x)) (ffn_base.py:53-77, model.py:128-129 / 147-148). need_split: whether the next
+        consumer reads the split-bf16 copy of x (a spatial block's gate GEMM, vec2patch); when it does not (a temporal
+        block or the positional embedding follows: they read the fp32 x), the second GEMM has a single output and stores
+        through the TMA epilogue."""
         with lib.scope("ffn"):
-            self._ffn_impl(g, P, name, x, xs, dev)
+            self._ffn_impl(g, P, name, x, xs if need_split else None, dev)
 
     def _ffn_impl(self, g, P, name, x, xs, dev):
         rows, d = g.bt * g.n, self.d
@@ -512,7 +526,7 @@ class FGT(nn.Module):
         self._split_qkv(P, name)
         q = self._buf(g, f"tp_q{T}", (g.zones * Lzl, d), dev, split=True)
         kv = self._buf(g, f"tp_kv{T}", (g.zones * Lz, 2 * d), dev, split=True)
-        att = self._buf(g, f"tp_att{T}", (g.zones * Lzl, d), dev, split=True)
+        att = self._buf(g, "att_tok", (g.bt * g.n, d), dev, split=True)   # attention output in token order
         lib.rownorm_bcast(x, ptrs, plane, gather=g.zone_map, rows_per_batch=Lzl, total_rows=g.zones * Lzl,
                           dst_batch_rows=Lz, dst_row0=off * zl, eps=LN_EPS, gamma=P[name + ".ln_g"],
                           beta=P[name + ".ln_b"])
@@ -528,9 +542,16 @@ class FGT(nn.Module):
         self._linear([lib.ASeg(s_all, d, g.zones * Lz)], P[name + ".kv"], g.zones * Lz, out_split=kv)
         lib.attention(q, kv, kv, att, batches=g.zones, heads=self.heads, Lq=Lzl, Lk=Lz, q_ld=d, k_ld=2 * d, v_ld=2 * d,
                       out_ld=d, q_batch_stride=Lzl * d, k_batch_stride=Lz * 2 * d, v_batch_stride=Lz * 2 * d,
-                      out_batch_stride=Lzl * d, scale=1.0 / math.sqrt(d // self.heads), v_off=d, tag=name)
-        self._linear([lib.ASeg(att, d, g.zones * Lzl)], P[name + ".o"], g.zones * Lzl, rowmap=g.zone_map, aux=x,
-                     aux_mode=lib.AUX_ADD, out_f32=x)
+                      out_batch_stride=Lzl * d, scale=1.0 / math.sqrt(d // self.heads), v_off=d, out_rowmap=g.zone_map,
+                      tag=name)
+        self._out_proj(g, P, name, att, x)
+
+    def _out_proj(self, g, P, name, att, x):
+        """x += output_linear(att) (attention_base.py:105, attention_flow.py:170; residual of model.py:127 / 146). The
+        attention kernel has already undone the zone / window regrouping in its store (out_rowmap), so this is a plain
+        row-major GEMM over the real tokens with the residual in its epilogue and a TMA tile store."""
+        rows = g.bt * g.n
+        self._linear([lib.ASeg(att, self.d, rows)], P[name + ".o"], rows, aux=x, aux_mode=lib.AUX_ADD, out_f32=x)
 
     def _split_qkv(self, P, name):
         """Q-only and K|V-only slices of the fused temporal projection (frame-sharded TMHSA: Q for the local
@@ -556,7 +577,7 @@ class FGT(nn.Module):
         s_loc = self._buf(g, f"ts_s{T}", (g.zones * Lqp, d), dev, split=True, zero=True)
         q = self._buf(g, f"ts_q{T}", (g.zones * Lqp, d), dev, split=True)
         kv = self._buf(g, f"ts_kv{T}", (g.zones * Lz, 2 * d), dev, split=True)
-        att = self._buf(g, f"ts_att{T}", (g.zones * Lzl, d), dev, split=True)
+        att = self._buf(g, "att_tok", (g.bt * g.n, d), dev, split=True)   # attention output in token order
         lib.rownorm(x, None, s_loc, gather=g.zone_map, rows_per_batch=Lzl, total_rows=g.zones * Lzl,
                     dst_batch_rows=Lqp, eps=LN_EPS, gamma=P[name + ".ln_g"], beta=P[name + ".ln_b"])
         s_all = parallel.allgather_zone_rows(s_loc.view(2, g.zones, Lqp, d), counts, zl, fs["group"], fs["work"])
@@ -565,25 +586,25 @@ class FGT(nn.Module):
         self._linear([lib.ASeg(s_all, d, g.zones * Lz)], P[name + ".kv"], g.zones * Lz, out_split=kv)
         lib.attention(q, kv, kv, att, batches=g.zones, heads=self.heads, Lq=Lzl, Lk=Lz, q_ld=d, k_ld=2 * d, v_ld=2 * d,
                       out_ld=d, q_batch_stride=Lqp * d, k_batch_stride=Lz * 2 * d, v_batch_stride=Lz * 2 * d,
-                      out_batch_stride=Lzl * d, scale=1.0 / math.sqrt(d // self.heads), v_off=d, tag=name)
-        self._linear([lib.ASeg(att, d, g.zones * Lzl)], P[name + ".o"], g.zones * Lzl, rowmap=g.zone_map, aux=x,
-                     aux_mode=lib.AUX_ADD, out_f32=x)
+                      out_batch_stride=Lzl * d, scale=1.0 / math.sqrt(d // self.heads), v_off=d, out_rowmap=g.zone_map,
+                      tag=name)
+        self._out_proj(g, P, name, att, x)
 
-    def _temporal(self, g, P, name, x, xs, dev):
+    def _temporal(self, g, P, name, x, xs, dev, need_split=True):
         """TemporalTransformer.forward (model.py:124-130) with TMHSA (attention_base.py:76-106)."""
         with lib.scope("tmhsa"):
             if getattr(self, "_fshard", None) is not None:
                 self._temporal_sharded(g, P, name, x, xs, dev)
             else:
                 self._tmhsa(g, P, name, x, dev)
-        self._ffn(g, P, name, x, xs, dev)
+        self._ffn(g, P, name, x, xs, dev, need_split)
 
     def _tmhsa(self, g, P, name, x, dev):
         """x += TMHSA(LN(x)): LayerNorm + zone gather, fused QKV GEMM, dense flash attention, out-projection."""
         d, rows_z = self.d, g.zones * g.Lz
         s_zm = self._buf(g, "t_s", (rows_z, d), dev, split=True)
         qkv = self._buf(g, "t_qkv", (rows_z, 3 * d), dev, split=True)
-        att = self._buf(g, "t_att", (rows_z, d), dev, split=True)
+        att = self._buf(g, "att_tok", (g.bt * g.n, d), dev, split=True)   # attention output in token order
         lib.rownorm(x, None, s_zm, gather=g.zone_map, rows_per_batch=rows_z, total_rows=rows_z,
                     dst_batch_rows=rows_z, eps=LN_EPS, gamma=P[name + ".ln_g"], beta=P[name + ".ln_b"])
         a = [lib.ASeg(s_zm, d, rows_z)]
@@ -591,15 +612,14 @@ class FGT(nn.Module):
         lib.attention(qkv, qkv, qkv, att, batches=g.zones, heads=self.heads, Lq=g.Lz, Lk=g.Lz, q_ld=3 * d, k_ld=3 * d,
                       v_ld=3 * d, out_ld=d, q_batch_stride=g.Lz * 3 * d, k_batch_stride=g.Lz * 3 * d,
                       v_batch_stride=g.Lz * 3 * d, out_batch_stride=g.Lz * d, scale=1.0 / math.sqrt(d // self.heads),
-                      k_off=d, v_off=2 * d, tag=name)
-        self._linear([lib.ASeg(att, d, rows_z)], P[name + ".o"], rows_z, rowmap=g.zone_map, aux=x,
-                     aux_mode=lib.AUX_ADD, out_f32=x)
+                      k_off=d, v_off=2 * d, out_rowmap=g.zone_map, tag=name)
+        self._out_proj(g, P, name, att, x)
 
-    def _spatial(self, g, P, name, x, xs, f, fs, dev):
+    def _spatial(self, g, P, name, x, xs, f, fs, dev, need_split=True):
         """SpatialTransformer.forward (model.py:144-149) with SWMHSA (attention_flow.py:115-171)."""
         with lib.scope("swmhsa"):
             self._swmhsa(g, P, name, x, xs, f, fs, dev)
-        self._ffn(g, P, name, x, xs, dev)
+        self._ffn(g, P, name, x, xs, dev, need_split)
 
     def _swmhsa(self, g, P, name, x, xs, f, fs, dev):
         """x += SWMHSA(x, f): flow gate, pooled global tokens, LayerNorms, Q|K and V GEMMs, windowed flash attention,
@@ -610,7 +630,7 @@ class FGT(nn.Module):
         qkn = self._buf(g, "s_qkn", (bt * g.R, d + df), dev, split=True, zero=True)
         vn = self._buf(g, "s_vn", (bt * g.R, d), dev, split=True, zero=True)
         qkv = self._buf(g, "s_qkv", (bt * g.R, 3 * d), dev, split=True)
-        att = self._buf(g, "s_att", (bt * g.nwp * 64, d), dev, split=True)
+        att = self._buf(g, "att_tok", (rows, d), dev, split=True)         # attention output in token order
         # flow re-weighting gate: f' = f * sigmoid(W_r [x; f] + b_r)   (attention_flow.py:126-128)
         self._linear([lib.ASeg(xs, d, rows), lib.ASeg(fs, df, rows)], P[name + ".gate"], rows, act=lib.ACT_SIGMOID,
                      aux=f, aux_mode=lib.AUX_MUL, out_f32=fp, bn=64 if rows <= 128 * 74 else None)  # 114 -> 228 tiles
@@ -626,9 +646,8 @@ class FGT(nn.Module):
         lib.attention(qkv, qkv, qkv, att, batches=bt, heads=self.heads, Lq=nl, Lk=g.R, Lk_rows=g.R, q_ld=3 * d,
                       k_ld=3 * d, v_ld=3 * d, out_ld=d, q_batch_stride=g.R * 3 * d, k_batch_stride=g.R * 3 * d,
                       v_batch_stride=g.R * 3 * d, out_batch_stride=nl * d, scale=1.0 / math.sqrt(d // self.heads),
-                      mode=1, glob_start=nl, glob_count=g.G, k_off=d, v_off=2 * d, tag=name)
-        self._linear([lib.ASeg(att, d, bt * nl)], P[name + ".o"], bt * nl, rowmap=g.win_map, aux=x,
-                     aux_mode=lib.AUX_ADD, out_f32=x)
+                      mode=1, glob_start=nl, glob_count=g.G, k_off=d, v_off=2 * d, out_rowmap=g.win_map, tag=name)
+        self._out_proj(g, P, name, att, x)
 
     # ------------------------------------------------------------------ forward
     def enable_cuda_graph(self, on=True):
@@ -688,8 +707,8 @@ class FGT(nn.Module):
                    seg_counts=[128, 192])
         self._conv(x0, 256, bt, OH, OW, P["enc12"], 3, out_split=e12, extra_seg=(e10, 512), groups=4,
                    seg_counts=[64, 128])
-        self._conv(x0, 256, bt, OH, OW, P["enc14"], 3, out_split=e14, extra_seg=(e12, 384), groups=8,
-                   seg_counts=[32, 48])
+        self._conv(x0, 256, bt, OH, OW, P["enc14"], 3, out_split=e14, extra_seg=(e12, 384), groups=2,
+                   seg_counts=[128, 192], alg_k=9 * (32 + 48))  # roofline accounting: the reference's 8-group conv
         self._conv(x0, 256, bt, OH, OW, P["enc16"], 3, out_split=enc, out_f32=enc_f, extra_seg=(e14, 256), groups=1,
                    seg_counts=[256, 256])
         # ---- flow encoder (model.py:206-212)
@@ -725,15 +744,16 @@ class FGT(nn.Module):
         self._cap("ftok", f)
         # ---- transformer (model.py:272-277)
         lib._scope[-1] = "pos_emb"
-        self._temporal(g, P, "t0", xa, xs, dev)
+        self._temporal(g, P, "t0", xa, xs, dev, need_split=False)   # the positional embedding re-creates the split copy
         self._cap("t0", xa)
         lib.dwconv3x3_res(xa, bt, g.h, g.w, self.d, P["pos_w"], P["pos_b"], xb, xs)
         x = xb
-        self._spatial(g, P, "s0", x, xs, f, fs, dev)
+        nb = len(self.transformer)
+        self._spatial(g, P, "s0", x, xs, f, fs, dev, need_split=nb == 0)   # a temporal block follows: it reads fp32 x
         self._cap("s0", x)
-        for i in range(len(self.transformer)):
-            self._temporal(g, P, f"t{i + 1}", x, xs, dev)
-            self._spatial(g, P, f"s{i + 1}", x, xs, f, fs, dev)
+        for i in range(nb):
+            self._temporal(g, P, f"t{i + 1}", x, xs, dev)                  # the spatial block's gate GEMM reads xs
+            self._spatial(g, P, f"s{i + 1}", x, xs, f, fs, dev, need_split=i == nb - 1)   # last: vec2patch reads xs
         self._cap("tok_final", x)
         # ---- vec2patch + skip (model.py:278-279)
         lib._scope[-1] = "vec2patch"

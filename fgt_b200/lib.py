@@ -50,7 +50,7 @@ class FgtAttnDesc(ctypes.Structure):
                 ("batches", ctypes.c_int), ("heads", ctypes.c_int), ("head_dim", ctypes.c_int),
                 ("Lq", ctypes.c_int), ("Lk", ctypes.c_int), ("Lk_rows", ctypes.c_int),
                 ("scale", ctypes.c_float), ("mode", ctypes.c_int),
-                ("glob_start", ctypes.c_int), ("glob_count", ctypes.c_int)]
+                ("glob_start", ctypes.c_int), ("glob_count", ctypes.c_int), ("out_rowmap", _c_p)]
 
 
 _lib = None
@@ -281,7 +281,8 @@ class ASeg:
 def gemm_tc(segs, w_split, N, *, kx=1, ky=1, kz=1, stride=1, dil=1, pad_x=0, pad_y=0, pad_z=0, groups=1,
             out_w, out_h=1, out_z=1, box_w=128, box_h=1, bn=128, bias=None, alpha=1.0, act=ACT_NONE,
             aux=None, aux_mode=AUX_NONE, out_f32=None, out_split=None, out_elem_offset=0,
-            os_z=0, os_y=0, os_x=None, os_c=1, rowmap=None, lin_batch=0, aux2=None, terms=3, out_f16=None, tag=""):
+            os_z=0, os_y=0, os_x=None, os_c=1, rowmap=None, lin_batch=0, aux2=None, terms=3, out_f16=None, alg_k=None,
+            tag=""):
     """Generic launcher for fgt_gemm_tc. Output strides are in elements; see include/fgt_b200.h.
     terms=1: the A segments' tensors and w_split are plain fp16 tensors (one plane); out_f16: plain fp16 output."""
     lib = load()
@@ -327,8 +328,10 @@ def gemm_tc(segs, w_split, N, *, kx=1, ky=1, kz=1, stride=1, dil=1, pad_x=0, pad
     d.lin_batch = lin_batch
     d.terms = terms
     # algorithmic work: every valid output position x N x (taps * real input channels), padding excluded
+    # (alg_k: the layer's true reduction length per output when the packed weight carries structural zeros, e.g. a
+    #  grouped convolution run as block-diagonal super-groups — zeros are not algorithmic work)
     m = out_w * out_h * out_z
-    kk = kx * ky * kz * k_real
+    kk = kx * ky * kz * k_real if alg_k is None else alg_k
     flops = 2.0 * m * N * kk
     nbytes = 4.0 * (m * k_real * stride * stride + N * kk + m * N)
     with _Prof("gemm_tc", tag, flops, nbytes):
@@ -337,7 +340,7 @@ def gemm_tc(segs, w_split, N, *, kx=1, ky=1, kz=1, stride=1, dil=1, pad_x=0, pad
 
 def attention(q, k, v, out, *, batches, heads, Lq, Lk, Lk_rows=None, q_ld, k_ld, v_ld, out_ld,
               q_batch_stride, k_batch_stride, v_batch_stride, out_batch_stride, scale, mode=0,
-              glob_start=0, glob_count=0, q_off=0, k_off=0, v_off=0, tag=""):
+              glob_start=0, glob_count=0, q_off=0, k_off=0, v_off=0, out_rowmap=None, tag=""):
     """fgt_attention launcher. q/k/v/out are split-bf16 row-major tensors; strides in elements; q_off/k_off/v_off
     are element offsets into the plane (e.g. when Q, K and V share one [rows, 3*C] projection buffer)."""
     lib = load()
@@ -350,6 +353,7 @@ def attention(q, k, v, out, *, batches, heads, Lq, Lk, Lk_rows=None, q_ld, k_ld,
     d.Lq, d.Lk = Lq, Lk
     d.Lk_rows = Lk if Lk_rows is None else Lk_rows
     d.scale, d.mode, d.glob_start, d.glob_count = scale, mode, glob_start, glob_count
+    d.out_rowmap = out_rowmap.data_ptr() if out_rowmap is not None else None
     keys = Lk if mode == 0 else 64 + glob_count
     flops = 4.0 * batches * heads * Lq * keys * 128
     nbytes = 4.0 * batches * heads * 128 * (2 * Lq + 2 * (Lk if mode == 0 else d.Lk_rows))

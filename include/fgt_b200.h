@@ -136,6 +136,8 @@ typedef struct {
   float scale;                  /* 1/sqrt(head_dim) */
   int mode;
   int glob_start, glob_count;   /* windowed mode */
+  const int* out_rowmap;        /* optional [batches * Lq]: query row -> row of a [rows, out_ld] output buffer (< 0 = drop);
+                                   out_batch_stride is ignored then. Undoes the zone / window regrouping in the store. */
 } FgtAttnDesc;
 
 int fgt_attention(const FgtAttnDesc* desc, fgt_stream_t stream);

@@ -360,14 +360,16 @@ def test_im2col_nchw_vs_torch(c0, c1, k, stride, pad, replicate, half):
     assert (got[..., k * k * cin:] == 0).all()
 
 
-@pytest.mark.parametrize("bt,th,tw,C", [(2, 20, 36, 40), (1, 22, 36, 40), (1, 5, 7, 8)])
-def test_fold_unfold_fused_equals_two_launches(bt, th, tw, C):
-    """fgt_fold_unfold == fgt_fold(normalize) -> fgt_unfold(relu), bit for bit (and both == nn.Fold / nn.Unfold, fp64)."""
+@pytest.mark.parametrize("bt,OH,OW,C", [(2, 60, 108, 40), (1, 64, 108, 40), (1, 16, 24, 8), (1, 180, 320, 40)])
+def test_fold_unfold_fused_equals_two_launches(bt, OH, OW, C):
+    """fgt_fold_unfold == fgt_fold(normalize) -> fgt_unfold(relu), bit for bit (and both == nn.Fold / nn.Unfold, fp64),
+    at the model's geometries (token grid = conv output size of the H/4 x W/4 map: the last rows of the padded map lie
+    under no patch)."""
     lib = _lib()
     dev = torch.device("cuda:0")
     torch.manual_seed(7)
     k, s, p = 7, 3, 3
-    OH, OW = (th - 1) * s + k - 2 * p, (tw - 1) * s + k - 2 * p
+    th, tw = (OH + 2 * p - k) // s + 1, (OW + 2 * p - k) // s + 1
     hid = torch.randn(bt * th * tw, k * k * C, device=dev)
     img = torch.empty(bt, OH, OW, C, device=dev)
     two = torch.full((2, bt * th * tw, k * k * C), 3.0, dtype=torch.bfloat16, device=dev)
