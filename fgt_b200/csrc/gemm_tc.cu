@@ -35,6 +35,7 @@ struct GemmParams {
   CUtensorMap a_maps[kMaxAMaps];
   CUtensorMap b_map;
   CUtensorMap out_map;  // epilogue TMA store: (C, X, Y, Z, plane) bf16 for a split output, (C, X, Y, Z) fp32
+  CUtensorMap aux_map;  // epilogue TMA load of the fp32 aux operand (residual / gate), same geometry as an fp32 out_map
   TapDesc taps[kMaxTaps];
   SegDesc segs[2];
   int num_taps, num_segs, num_maps, k_iters;
@@ -44,6 +45,7 @@ struct GemmParams {
   int planes;   // 2: split-bf16 operands, 3 MMAs per K step; 1: single-plane fp16 operands, 1 MMA per K step
   int out_half; // the 16-bit output is ONE plane of fp16 (input of a 1-term layer) instead of split-bf16
   int tma_out;  // epilogue stores through shared memory + TMA (single output, unit channel stride, no rowmap)
+  int aux_tma;    // the aux tile is fetched into the staging panels by TMA (fp32 output launches) instead of per-row loads
   int stg_slots;  // staging ring of the TMA epilogue: 1, 2 or 4 slots (a slot = the panels of one 64-channel chunk)
   int stg_slot_bytes;
   int box_w, box_h, a_rows;
@@ -246,7 +248,7 @@ __device__ __forceinline__ void epi_chunk(const EpiArgs& e, const uint32_t (&raw
 // the aux operand for 32 consecutive channels of one output row; channels >= N (N tail) skip their aux loads.
 template <int kExt>
 __device__ __forceinline__ void epi_math(const EpiArgs& e, const uint32_t (&raw)[32], const float* sb, long long off,
-                                         int col0, bool valid, float (&v)[32]) {
+                                         int col0, bool valid, float (&v)[32], uint32_t aux_smem = 0u, uint32_t sw = 0u) {
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const float4 b = *reinterpret_cast<const float4*>(sb + 4 * q);
@@ -258,7 +260,10 @@ __device__ __forceinline__ void epi_math(const EpiArgs& e, const uint32_t (&raw)
   const long long o = off + col0;
   const bool aux_ok = valid && e.aux_mode != FGT_AUX_NONE;
   float4 a[8];
-  if (aux_ok) {
+  if (aux_ok && aux_smem) {  // the tile's aux values were fetched by TMA into this thread's swizzled panel row
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a[q] = ld_shared_f4(aux_smem + ((static_cast<uint32_t>(q) ^ sw) << 4));
+  } else if (aux_ok) {
     const float4* ap = reinterpret_cast<const float4*>(e.aux + o);
 #pragma unroll
     for (int q = 0; q < 8; ++q)
@@ -366,6 +371,11 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     for (int i = 0; i < p.num_maps; ++i) tma_prefetch_desc(&p.a_maps[i]);
     tma_prefetch_desc(&p.b_map);
     if (p.tma_out) tma_prefetch_desc(&p.out_map);
+    if (p.aux_tma) {
+      tma_prefetch_desc(&p.aux_map);
+      mbar_init(bar_base + 8u * 30, 1);  // aux tile landed (one load in flight at a time)
+      fence_mbar_init();
+    }
   }
   if (warp == 1) tmem_alloc(tmem_slot, static_cast<uint32_t>(n_acc * p.bn_p2));
   tc_fence_before();
@@ -542,6 +552,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
         const int x0 = tx * p.box_w, y0 = p.linear ? 0 : ty * p.box_h, zz = p.linear ? 0 : z;
         const uint32_t row_off = static_cast<uint32_t>(r) * 128u;
         const uint32_t sw = static_cast<uint32_t>(r & 7);
+        const uint32_t aux_bar = bar_base + 8u * 30;
         for (int c0 = 0; c0 < e_bn && n0 + c0 < e_N; c0 += 64, ++stg_it) {
           // ring of staging slots: this chunk's slot is free once all but the (slots - 1) most recent store groups
           // have finished reading shared memory
@@ -550,15 +561,26 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
             if (p.stg_slots == 1) bulk_wait_read<0>();
             else if (p.stg_slots == 2) bulk_wait_read<1>();
             else bulk_wait_read<3>();
+            if (p.aux_tma) {  // fetch this chunk's aux tile (two 32-column fp32 panels) into the slot it will be stored from
+              const bool two = n0 + c0 + 32 < e_N;
+              mbar_expect_tx(aux_bar, static_cast<uint32_t>(p.a_rows) * 128u * (two ? 2u : 1u));
+              tma_load_4d(stg_base, &p.aux_map, aux_bar, n0 + c0, x0, y0, zz);
+              if (two) tma_load_4d(stg_base + kAPlaneBytes, &p.aux_map, aux_bar, n0 + c0 + 32, x0, y0, zz);
+            }
           }
-          asm volatile("bar.sync 1, 128;\n" ::: "memory");
+          if (p.aux_tma) {
+            mbar_wait(aux_bar, stg_it & 1u);  // implies the slot was free: the loads were issued after the read-wait
+          } else {
+            asm volatile("bar.sync 1, 128;\n" ::: "memory");
+          }
 #pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
             uint32_t raw[32];
             tmem_ld32(t_row + c0 + hf * 32, raw);
             tmem_ld_wait();
             float v[32];
-            epi_math<kExt>(ep, raw, sbias + c0 + hf * 32, off, n0 + c0 + hf * 32, valid, v);
+            epi_math<kExt>(ep, raw, sbias + c0 + hf * 32, off, n0 + c0 + hf * 32, valid, v,
+                           p.aux_tma ? stg_base + hf * kAPlaneBytes + row_off : 0u, sw);
             if (ep.out_hi && ep.out_half) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -640,6 +662,7 @@ static int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b
 
 static bool g_gemm_trace_on = false;  // debugging aid, see fgt_debug_gemm_trace()
 static bool g_gemm_direct_epilogue = false;  // debugging aid: force the register-store epilogue (A/B comparisons)
+static bool g_gemm_direct_aux = false;       // debugging aid: aux operand by per-row global loads even on the TMA path
 
 int gemm_tc_launch(const FgtGemmDesc& d, cudaStream_t stream) {
   FGT_REQUIRE(d.num_segs >= 1 && d.num_segs <= 2, FGT_ERR_ARG, "gemm_tc: num_segs=%d", d.num_segs);
@@ -791,6 +814,17 @@ int gemm_tc_launch(const FgtGemmDesc& d, cudaStream_t stream) {
     int rc = d.out_hi ? encode_map_bf16(&p.out_map, d.out_hi, 5, dims, str, box)
                       : encode_map_f32(&p.out_map, d.out_f32, 4, dims, str, box);
     if (rc) return rc;
+    // fp32 output + an aux operand that is a plain fp32 tensor addressed like the output (residual add, gate multiply):
+    // fetch the aux tile by TMA as well — per-row 16-byte loads of a row-per-thread epilogue touch 32 lines per request
+    p.aux_tma = (!d.out_hi && d.aux && !g_gemm_direct_aux &&
+                 (d.aux_mode == FGT_AUX_ADD || d.aux_mode == FGT_AUX_MUL || d.aux_mode == FGT_AUX_ADD_PRE ||
+                  d.aux_mode == FGT_AUX_ADD_RELU))
+                    ? 1
+                    : 0;
+    if (p.aux_tma) {
+      rc = encode_map_f32(&p.aux_map, d.aux, 4, dims, str, box);
+      if (rc) return rc;
+    }
   }
 
   const uint32_t stage_bytes = static_cast<uint32_t>(p.planes) * (kAPlaneBytes + static_cast<uint32_t>(d.bn) * 128u);
@@ -858,7 +892,8 @@ extern "C" int fgt_gemm_tc(const FgtGemmDesc* desc, fgt_stream_t stream) {
 // issued}, MMA {tile start, accumulator buffer free, first operands landed, last MMA committed}, epilogue {tile start,
 // accumulator complete, stores issued}.
 extern "C" int fgt_debug_gemm_direct_epilogue(int on) {
-  fgt::g_gemm_direct_epilogue = on != 0;
+  fgt::g_gemm_direct_epilogue = (on & 1) != 0;
+  fgt::g_gemm_direct_aux = (on & 2) != 0;
   return FGT_OK;
 }
 

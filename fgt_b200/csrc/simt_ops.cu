@@ -145,7 +145,7 @@ struct NormDests {
   int n;
 };
 
-__global__ void rownorm_kernel(const float* __restrict__ a, int ca, int lda, const float* __restrict__ b, int cb,
+__global__ void __launch_bounds__(256, 4) rownorm_kernel(const float* __restrict__ a, int ca, int lda, const float* __restrict__ b, int cb,
                                int ldb, const int* __restrict__ gather, int rows_per_batch, long long total_rows,
                                int dst_batch_rows, int dst_row0, const float* __restrict__ gamma,
                                const float* __restrict__ beta, const NormDests dst, long long plane, float eps) {
@@ -393,12 +393,15 @@ __global__ void fold_unfold_kernel(const float* __restrict__ hid, int bt, int th
   if (threadIdx.x >= C4) return;
   const int hidden = kh * kw * C;
   const int c = threadIdx.x * 4;
-  // rows y in [-pd, OH + pd): the padded rows only produce zeros
+  // rows y in [-pd, OH + pd): the padded rows only produce zeros. blockIdx.y splits the row into gridDim.y segments
+  // (more blocks in flight: the kernel is latency-bound with one block per row)
   const int HP = OH + 2 * pd;
   const int b = blockIdx.x / HP, y = blockIdx.x - b * HP - pd;
   const bool y_in = y >= 0 && y < OH;
   const int ty_hi = min((y + pd) / st, th - 1);
-  for (int x = static_cast<int>(threadIdx.y) - pd; x < OW + pd; x += blockDim.y) {
+  const int seg = (OW + 2 * pd + gridDim.y - 1) / gridDim.y;
+  const int x_lo = static_cast<int>(blockIdx.y) * seg - pd, x_hi = min(x_lo + seg, OW + pd);
+  for (int x = x_lo + static_cast<int>(threadIdx.y); x < x_hi; x += blockDim.y) {
     const bool in = y_in && x >= 0 && x < OW;
     const int tx_hi = min((x + pd) / st, tw - 1);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -647,7 +650,7 @@ extern "C" int fgt_fold_unfold(const float* hid, int bt, int th, int tw, int C, 
               "fold_unfold: patches do not cover the %dx%d map", OH, OW);
   const int gx = (C / 4 + 1) / 2 * 2;
   const dim3 blk(gx, 256 / gx);
-  launch_k(fold_unfold_kernel, dim3(bt * (OH + 2 * pad)), dim3(blk), 0, reinterpret_cast<cudaStream_t>(stream), hid, bt, th, tw, C, kh,
+  launch_k(fold_unfold_kernel, dim3(bt * (OH + 2 * pad), 4), dim3(blk), 0, reinterpret_cast<cudaStream_t>(stream), hid, bt, th, tw, C, kh,
            kw, stride, pad, OH, OW, relu, reinterpret_cast<__nv_bfloat16*>(out_hi), out_plane);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;

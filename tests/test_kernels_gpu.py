@@ -83,7 +83,7 @@ def test_tma_epilogue_bit_equal_to_register_epilogue():
     L = lib.load()
     L.fgt_debug_gemm_direct_epilogue.argtypes = [ctypes.c_int]
     outs = []
-    for direct in (0, 1):
+    for direct in (0, 1, 2):   # 0: TMA epilogue + TMA-fetched aux tile, 1: register epilogue, 2: TMA epilogue + per-row aux loads
         L.fgt_debug_gemm_direct_epilogue(direct)
         try:
             o32 = torch.zeros(M, N, device=dev)
@@ -97,6 +97,20 @@ def test_tma_epilogue_bit_equal_to_register_epilogue():
             L.fgt_debug_gemm_direct_epilogue(0)
         outs.append((o32, osp))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert torch.equal(outs[0][0], outs[2][0]) and torch.equal(outs[0][1], outs[2][1])
+    # in-place residual (aux == out), the out-projection / FFN pattern
+    x0 = torch.randn(M, N, device=dev)
+    res = []
+    for direct in (0, 1):
+        L.fgt_debug_gemm_direct_epilogue(direct)
+        try:
+            x = x0.clone()
+            lib.gemm_tc([lib.ASeg(a_s, K, M)], w_s, N, out_w=M, bn=128, bias=b, out_f32=x, aux=x, aux_mode=lib.AUX_ADD)
+            torch.cuda.synchronize()
+        finally:
+            L.fgt_debug_gemm_direct_epilogue(0)
+        res.append(x)
+    assert torch.equal(res[0], res[1])
 
 
 def test_linear_rowmap_and_transposed_store():
