@@ -368,17 +368,21 @@ def main():
         assert n_out == args.steps
         return parallel.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps, st
 
-    def timed_frame_sharded(tw):
+    def timed_frame_sharded(tw, fh=H, fw=W, steps=10):
         """N>1: ONE tw-frame window sharded by frames over the ranks (FGT.enable_frame_sharding: P2P exchange fused
         into the LayerNorm kernel vs NCCL all-gather) — strong scaling of a single forward; the one-GPU time of
         the same window is measured in the same run (every rank runs it; max over ranks)."""
         mine = parallel.shard_items(tw, rank, world)
-        clip0 = synth.fgt_inputs(seed=3, t=tw, H=H, W=W)      # every rank: the same window, its own frames
+        clip0 = synth.fgt_inputs(seed=3, t=tw, H=fh, W=fw)    # every rank: the same window, its own frames
         full = [t.to(dev) for t in clip0]
         model.net.enable_frame_sharding(None)
         model.net.enable_cuda_graph(True)
-        ms1, _ = timed(lambda: model(*full), steps=10, warmup=3)
-        res = {"frames": tw, "ms_one_gpu": ms1, "frames_per_rank": parallel.frame_counts(tw, world)}
+        ms1, _ = timed(lambda: model(*full), steps=steps, warmup=3)
+        del full
+        model.net._drop_graphs()                               # (the captured graph holds the workspaces' addresses)
+        model.net._geo.clear()                                 # drop the full window's workspaces (30+ GB at 720p)
+        torch.cuda.empty_cache()
+        res = {"frames": tw, "size": f"{fw}x{fh}", "ms_one_gpu": ms1, "frames_per_rank": parallel.frame_counts(tw, world)}
         if not mine:
             return res
         part = [t[:, mine[0]:mine[-1] + 1].contiguous().to(dev) for t in clip0]
@@ -386,7 +390,7 @@ def main():
             model.net.enable_frame_sharding(tw, exchange=exchange)
             model.net.enable_cuda_graph(exchange == "p2p")   # kernels only -> replayable; NCCL calls stay eager
             try:
-                res["ms_" + exchange], _ = timed(lambda: model(*part), steps=10, warmup=3)
+                res["ms_" + exchange], _ = timed(lambda: model(*part), steps=steps, warmup=3)
             finally:
                 model.net.enable_cuda_graph(False)
                 model.net.enable_frame_sharding(None)
@@ -490,6 +494,17 @@ def main():
             except Exception as exc:  # noqa: BLE001 - reported, never fatal for the main line
                 print(f"[bench] frame-sharded measurement (T={tw}) failed: {exc}", file=sys.stderr)
                 fshard[f"T{tw}"] = {"error": str(exc)[:200]}
+        # BASELINE config 5's shape (1280x720, window-partition + global-token path, 21-26 k-key temporal zones): where a
+        # rank's share of a window is heavy enough for frame sharding to pay at 8 GPUs
+        if os.environ.get("FGT_BENCH_FS_720P", "1") != "0" and world <= 16:
+            try:
+                fshard["T16_1280x720"] = timed_frame_sharded(16, 720, 1280, steps=5)
+            except Exception as exc:  # noqa: BLE001
+                print(f"[bench] frame-sharded measurement (720p) failed: {exc}", file=sys.stderr)
+                fshard["T16_1280x720"] = {"error": str(exc)[:200]}
+            finally:
+                model.net._geo.clear()
+                torch.cuda.empty_cache()
     if rank == 0:
         frames = T * world
         h2d = sum(t.numel() * t.element_size() for t in host)

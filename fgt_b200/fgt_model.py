@@ -163,6 +163,17 @@ def _pick_bn(n_per_group, groups, name=""):
     return 128
 
 
+def _fill_sms(bn, n_total, m_positions, groups=1, n_sms=148):
+    """Short windows (a frame-sharded rank's 1-3 frames, the driver's t = 6 window) leave most SMs without a tile when
+    the channel tile is 128 wide, and a sub-wave GEMM takes as long as its one tile: halve the tile while the launch
+    covers at most half a wave (down to 64, the narrowest tile of the TMA-store epilogue)."""
+    m_tiles = -(-m_positions // 128)
+    while (bn > 64 and bn % 32 == 0 and 2 * m_tiles * -(-n_total // bn) <= n_sms   # at most half a wave
+           and (groups == 1 or (n_total // groups) % (bn // 2) == 0)):
+        bn //= 2
+    return bn
+
+
 class FGT(nn.Module):
     """Parameter layout of FGT (model.py:196-246) + the sm_100a forward schedule (model.py:249-283)."""
 
@@ -433,7 +444,8 @@ class FGT(nn.Module):
         else:
             strides = dict(os_z=oh * ow * N, os_y=ow * N, os_x=N, os_c=1)
         lib.gemm_tc(segs, wp["w"], N, kx=k, ky=k, stride=stride, pad_x=pad, pad_y=pad, groups=groups, out_w=ow,
-                    out_h=oh, out_z=n, box_w=bw, box_h=bh, bn=_pick_bn(N // groups, groups, wp["name"]), bias=wp["b"], act=act,
+                    out_h=oh, out_z=n, box_w=bw, box_h=bh,
+                    bn=_fill_sms(_pick_bn(N // groups, groups, wp["name"]), N, n * oh * ow, groups), bias=wp["b"], act=act,
                     out_f32=out_f32, out_split=out_split, out_f16=out_f16, tag=wp["name"], terms=terms, alg_k=alg_k,
                     **strides)
         return oh, ow
@@ -453,8 +465,8 @@ class FGT(nn.Module):
 
     @staticmethod
     def _linear(segs, wp, rows, bn=None, **kw):
-        lib.gemm_tc(segs, wp["w"], wp["N"], out_w=rows, bn=bn or _pick_bn(wp["N"], 1, wp["name"]), bias=wp["b"],
-                    tag=wp["name"], **kw)
+        lib.gemm_tc(segs, wp["w"], wp["N"], out_w=rows,
+                    bn=bn or _fill_sms(_pick_bn(wp["N"], 1, wp["name"]), wp["N"], rows), bias=wp["b"], tag=wp["name"], **kw)
 
     def _ffn(self, g, P, name, x, xs, dev, need_split=True):
         """x += FusionFeedForward(LN(x)) (ffn_base.py:53-77, model.py:128-129 / 147-148). need_split: whether the next
