@@ -72,26 +72,23 @@ __global__ void im2col_nchw_kernel(const float* __restrict__ s0, int c0, const f
   const int b = blockIdx.x / OH, oy = blockIdx.x - b * OH;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
   const long long HWl = static_cast<long long>(H) * W;
-  const int row_elems = cin * Wp;
-  for (int idx = tid; idx < k * row_elems; idx += nthr) {
-    const int ky = idx / row_elems;
-    const int r = idx - ky * row_elems;
-    const int c = r / Wp;
-    const int xx = r - c * Wp;
-    int y = oy * stride + ky - pad, x = xx - pad;
-    bool ok = true;
-    if (replicate) {
-      y = min(max(y, 0), H - 1);
+  // staged row rc = ky*cin + c: one warp per row, lanes along x (no per-element integer division — the first version of
+  // this loop spent 4x the instructions of the gather on idx / row_elems, r / Wp)
+  const int lane = tid & 31, wrp = tid >> 5, nwarp = nthr >> 5;
+  for (int rc = wrp; rc < k * cin; rc += nwarp) {
+    const int ky = rc / cin, c = rc - ky * cin;
+    int y = oy * stride + ky - pad;
+    const bool y_ok = replicate || (y >= 0 && y < H);
+    y = min(max(y, 0), H - 1);
+    const float* src = (c < c0) ? s0 + (static_cast<long long>(b) * c0 + c) * HWl + static_cast<long long>(y) * W
+                                : s1 + (static_cast<long long>(b) * c1 + (c - c0)) * HWl + static_cast<long long>(y) * W;
+    float* dst = srow + rc * Wp;
+    for (int xx = lane; xx < Wp; xx += 32) {
+      int x = xx - pad;
+      const bool ok = y_ok && (replicate || (x >= 0 && x < W));
       x = min(max(x, 0), W - 1);
-    } else {
-      ok = y >= 0 && y < H && x >= 0 && x < W;
+      dst[xx] = ok ? fmaf(__ldg(src + x), scale, shift) : 0.f;
     }
-    float v = 0.f;
-    if (ok)
-      v = fmaf((c < c0) ? __ldg(s0 + (static_cast<long long>(b) * c0 + c) * HWl + static_cast<long long>(y) * W + x)
-                        : __ldg(s1 + (static_cast<long long>(b) * c1 + (c - c0)) * HWl + static_cast<long long>(y) * W + x),
-               scale, shift);
-    srow[idx] = v;
   }
   // this thread's 8 output channels: ch = (ky*k + kx)*cin + c  ->  offset of (ky, c, kx) in the staged rows
   const int g = threadIdx.x;
@@ -157,7 +154,9 @@ __global__ void __launch_bounds__(256, 4) rownorm_kernel(const float* __restrict
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const int nvec = C / 4;
   for (long long d = warp_id; d < total_rows; d += nwarps) {
-    const long long bidx = d / rows_per_batch;
+    // 32-bit division when the row count allows it (always, in this model): the 64-bit one is ~80 instructions per row
+    const long long bidx = (total_rows <= 0x7fffffffLL) ? static_cast<long long>(static_cast<int>(d) / rows_per_batch)
+                                                        : d / rows_per_batch;
     const long long drow = bidx * dst_batch_rows + dst_row0 + (d - bidx * rows_per_batch);
     const long long ooff = drow * C;
     long long src = d;
@@ -259,17 +258,24 @@ __global__ void dwconv3_res_kernel(const float* __restrict__ x, int bt, int h, i
                                    float* __restrict__ out, __nv_bfloat16* __restrict__ hi, long long plane) {
   pdl_launch_dependents();
   pdl_wait();
-  // one thread = 4 consecutive channels of one token: float4 loads of the 3x3 neighbourhood (coalesced along c)
+  // one block = one token row (frame, py); one thread = 4 consecutive channels, striding over the row's tokens: float4
+  // loads of the 3x3 neighbourhood (coalesced along c), weights and bias of the thread's channels held in registers
   const int C4 = C / 4;
-  const long long total = static_cast<long long>(bt) * h * w * C4;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % C4) * 4;
-    const long long t = i / C4;
-    const int px = static_cast<int>(t % w);
-    const int py = static_cast<int>((t / w) % h);
-    const long long f = t / (static_cast<long long>(w) * h);
-    float4 acc = __ldg(reinterpret_cast<const float4*>(bias + c));
+  const long long f = blockIdx.x / h;
+  const int py = blockIdx.x - static_cast<int>(f) * h;
+  for (int cq = threadIdx.x; cq < C4; cq += blockDim.x) {
+   const int c = cq * 4;
+   float wreg[4][9];
+#pragma unroll
+   for (int i = 0; i < 4; ++i)
+#pragma unroll
+     for (int tap = 0; tap < 9; ++tap) wreg[i][tap] = __ldg(wt + (c + i) * 9 + tap);
+   const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c));
+   const int seg = (w + gridDim.y - 1) / gridDim.y;
+   const int px_end = min(w, static_cast<int>(blockIdx.y + 1) * seg);
+   for (int px = blockIdx.y * seg + threadIdx.y; px < px_end; px += blockDim.y) {
+    const long long t = (f * h + py) * w + px;
+    float4 acc = b4;
     float4 centre = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
@@ -282,16 +288,17 @@ __global__ void dwconv3_res_kernel(const float* __restrict__ x, int bt, int h, i
         const float4 v = __ldg(reinterpret_cast<const float4*>(x + ((f * h + y) * w + xx) * C + c));
         if (ky == 1 && kx == 1) centre = v;
         const int tap = ky * 3 + kx;
-        acc.x += __ldg(wt + (c + 0) * 9 + tap) * v.x;
-        acc.y += __ldg(wt + (c + 1) * 9 + tap) * v.y;
-        acc.z += __ldg(wt + (c + 2) * 9 + tap) * v.z;
-        acc.w += __ldg(wt + (c + 3) * 9 + tap) * v.w;
+        acc.x += wreg[0][tap] * v.x;
+        acc.y += wreg[1][tap] * v.y;
+        acc.z += wreg[2][tap] * v.z;
+        acc.w += wreg[3][tap] * v.w;
       }
     }
     const float4 v = make_float4(acc.x + centre.x, acc.y + centre.y, acc.z + centre.z, acc.w + centre.w);
     const long long o = t * C + c;
     *reinterpret_cast<float4*>(out + o) = v;
     if (hi) store_split4(hi + o, hi + plane + o, v.x, v.y, v.z, v.w);
+   }
   }
 }
 
@@ -608,8 +615,8 @@ extern "C" int fgt_dwconv3x3_res(const float* x, int bt, int h, int w, int C, co
                                  float* out, void* out_hi, long long out_plane, fgt_stream_t stream) {
   FGT_REQUIRE(x && weight && bias && out, FGT_ERR_ARG, "dwconv3x3_res: null argument");
   FGT_REQUIRE(C % 4 == 0, FGT_ERR_ARG, "dwconv3x3_res: C=%d must be a multiple of 4", C);
-  const long long total = static_cast<long long>(bt) * h * w * (C / 4);
-  launch_k(dwconv3_res_kernel, dim3(grid_for(total, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), 
+  const int tx = (C / 4) < 128 ? (C / 4 + 31) / 32 * 32 : 128;   // threads along channels (x), tokens of the row along y
+  launch_k(dwconv3_res_kernel, dim3(bt * h, w >= 16 ? 4 : 1), dim3(tx, 256 / tx > 0 ? 256 / tx : 1), 0, reinterpret_cast<cudaStream_t>(stream), 
       x, bt, h, w, C, weight, bias, out, reinterpret_cast<__nv_bfloat16*>(out_hi), out_plane);
   FGT_CUDA(cudaGetLastError());
   return FGT_OK;
