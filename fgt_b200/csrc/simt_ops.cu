@@ -310,6 +310,43 @@ __global__ void dwconv3_res_kernel(const float* __restrict__ x, int bt, int h, i
 //   img[b,y,x,c] = scale(y,x) * sum_{patches covering (y,x)} hid[b, token, p, c]   (+ add[b,y,x,c])
 // scale = 1/coverage-count when `normalize` (FusionFeedForward) else 1 (Vec2Patch).
 // ------------------------------------------------------------------------------------------
+// Sum of the patch entries covering pixel (y, x) of frame b, for kernels with ceil(k / stride) <= 3 (the model's 7x7 /
+// stride 3): the <= 3x3 candidate loads are issued together (predicated) and added in the order of the general loops
+// below (ty, tx descending) — the looped form keeps ONE load in flight per warp (each add waits for its load), which
+// bounded both fold kernels at ~2.8-3.4 TB/s.
+__device__ __forceinline__ float4 fold_gather3(const float* __restrict__ hid, int b, int th, int tw, int hidden, int C,
+                                               int c, int kh, int kw, int st, int pd, int y, int x, int ty_hi,
+                                               int tx_hi, int& cnt) {
+  float4 v[3][3];
+  bool ok[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int ty = ty_hi - i, ky = y + pd - st * ty;
+    const bool oky = ty >= 0 && ky < kh;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int tx = tx_hi - j, kx = x + pd - st * tx;
+      ok[i][j] = oky && tx >= 0 && kx < kw;
+      // candidates outside the coverage load a fixed valid address instead (an L1 hit, result unused): unconditional
+      // loads are what lets the compiler issue all nine before the first add
+      const float* src = ok[i][j] ? hid + ((static_cast<long long>(b) * th + ty) * tw + tx) * hidden + (ky * kw + kx) * C + c
+                                  : hid + c;
+      v[i][j] = __ldg(reinterpret_cast<const float4*>(src));
+    }
+  }
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  cnt = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      if (ok[i][j]) {
+        acc.x += v[i][j].x; acc.y += v[i][j].y; acc.z += v[i][j].z; acc.w += v[i][j].w;
+        ++cnt;
+      }
+  return acc;
+}
+
 __global__ void fold_kernel(const float* __restrict__ hid, int bt, int th, int tw, int C, int kh, int kw, int st,
                             int pd, int OH, int OW, int normalize, const float* __restrict__ add,
                             float* __restrict__ out, __nv_bfloat16* __restrict__ hi, long long plane) {
@@ -323,11 +360,13 @@ __global__ void fold_kernel(const float* __restrict__ hid, int bt, int th, int t
   const int c = threadIdx.x * 4;
   if (threadIdx.x >= C4) return;
   const int ty_hi = min((y + pd) / st, th - 1);
+  const bool cov3 = (kh + st - 1) / st <= 3 && (kw + st - 1) / st <= 3;
   for (int x = threadIdx.y; x < OW; x += blockDim.y) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int cnt = 0;
     const int tx_hi = min((x + pd) / st, tw - 1);
-    for (int ty = ty_hi; ty >= 0; --ty) {
+    if (cov3) acc = fold_gather3(hid, b, th, tw, hidden, C, c, kh, kw, st, pd, y, x, ty_hi, tx_hi, cnt);
+    else for (int ty = ty_hi; ty >= 0; --ty) {
       const int ky = y + pd - st * ty;
       if (ky >= kh) break;
       for (int tx = tx_hi; tx >= 0; --tx) {
@@ -406,6 +445,7 @@ __global__ void fold_unfold_kernel(const float* __restrict__ hid, int bt, int th
   const int b = blockIdx.x / HP, y = blockIdx.x - b * HP - pd;
   const bool y_in = y >= 0 && y < OH;
   const int ty_hi = min((y + pd) / st, th - 1);
+  const bool cov3 = (kh + st - 1) / st <= 3 && (kw + st - 1) / st <= 3;
   const int seg = (OW + 2 * pd + gridDim.y - 1) / gridDim.y;
   const int x_lo = static_cast<int>(blockIdx.y) * seg - pd, x_hi = min(x_lo + seg, OW + pd);
   for (int x = x_lo + static_cast<int>(threadIdx.y); x < x_hi; x += blockDim.y) {
@@ -414,7 +454,8 @@ __global__ void fold_unfold_kernel(const float* __restrict__ hid, int bt, int th
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     int cnt = 0;
     if (in) {
-      for (int ty = ty_hi; ty >= 0; --ty) {
+      if (cov3) acc = fold_gather3(hid, b, th, tw, hidden, C, c, kh, kw, st, pd, y, x, ty_hi, tx_hi, cnt);
+      else for (int ty = ty_hi; ty >= 0; --ty) {
         const int ky = y + pd - st * ty;
         if (ky >= kh) break;
         for (int tx = tx_hi; tx >= 0; --tx) {
