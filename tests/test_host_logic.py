@@ -158,3 +158,95 @@ def test_c_abi_rejects_bad_arguments_without_touching_the_gpu():
     assert L.fgt_poisson_graph_destroy(None) == 0   # destroying nothing is not an error
     with pytest.raises(RuntimeError, match="fgt_plane_max"):
         lib.check(L.fgt_plane_max(None, 1, 16, None, None), "fgt_plane_max")
+
+
+# ------------------------------------------------------------------------------------------ round 2 host logic
+def test_pack_weight_half_and_im2col():
+    """1-term (fp16 single-plane) packing of the flow branch keeps pack_weight's K order; the im2col packing follows
+    fgt_im2col_nchw's K index (ky*k + kx)*cin + c."""
+    w = torch.randn(6, 10, 3, 3)
+    h = packing.pack_weight(w, [4, 6], half=True)
+    assert h.dtype == torch.float16 and h.shape == (6, 9 * 128)
+    s = lib.from_split(packing.pack_weight(w, [4, 6]))
+    assert torch.allclose(h.float(), s, rtol=2e-3, atol=1e-4)          # same layout, fp16 vs split-bf16 rounding
+    w5 = torch.randn(8, 2, 5, 5)
+    p = lib.from_split(packing.pack_weight_im2col(w5, cpad=64)).reshape(8, 64)
+    for ky, kx, c in [(0, 0, 0), (0, 0, 1), (2, 3, 1), (4, 4, 0)]:
+        assert torch.allclose(p[:, (ky * 5 + kx) * 2 + c], w5[:, c, ky, kx], rtol=1e-4, atol=1e-6)
+    assert p[:, 50:].abs().max() == 0
+    ph = packing.pack_weight_im2col(w5, cpad=64, half=True)
+    assert ph.dtype == torch.float16 and ph.shape == (8, 64)
+
+
+def test_fill_sms_tile_choice():
+    """Channel-tile width by wave fill (fgt_model._fill_sms): 128 wide when the launch covers more than half a wave,
+    halved (never below 64, never across a group boundary) when it does not."""
+    from fgt_b200.fgt_model import _fill_sms
+    assert _fill_sms(128, 512, 7200) == 128             # 57 x 4 = 228 tiles: > half a wave of 148 SMs
+    assert _fill_sms(128, 512, 1440) == 64              # 12 x 4 = 48 tiles: 2 x 48 <= 148 -> 64 wide (96 tiles)
+    assert _fill_sms(128, 512, 128) == 64               # a single row tile still stops at 64
+    assert _fill_sms(64, 512, 128) == 64
+    assert _fill_sms(128, 1536, 2160) == 128            # 17 x 12 = 204 tiles
+    assert _fill_sms(128, 256, 720, groups=8) == 128    # 32 channels per group: a 64-wide tile must hold whole groups
+    assert _fill_sms(128, 512, 720, groups=2) == 64
+
+
+def test_bench_module_flops_match_survey():
+    """bench.py's per-module denominators are SURVEY.md section 8(d)'s: 41.64 GFLOP per TMHSA layer, 3.091 GFLOP per
+    frame per SWMHSA layer, 28.9 GFLOP per FFN layer at T = 10."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    f = bench.module_flops(10)
+    assert abs(f["tmhsa"] / 1e9 - 41.64) < 0.01
+    assert abs(f["swmhsa"] / 1e10 - 3.091) < 0.001
+    assert abs(f["ffn"] / 1e9 - 28.9) < 0.01
+    f2 = bench.module_flops(20)
+    assert abs(f2["ffn"] / f["ffn"] - 2) < 1e-12 and f2["tmhsa"] / f["tmhsa"] > 2   # ∝ T and ∝ T + T^2
+    # the arms of config 2 must describe the same workload (the driver compares the dicts)
+    assert bench.config_dict(1).keys() == bench.config_dict(8).keys()
+    assert bench.config_dict(1)["workload"] == bench.config_dict(8)["workload"]
+
+
+def test_c_abi_rejects_bad_arguments_round2_entry_points():
+    """Same contract for the entry points added in round 2 (include/fgt_b200.h): validation precedes any CUDA call."""
+    L = lib.load()
+    L.fgt_last_error.restype = ctypes.c_char_p
+    one = ctypes.c_void_p(8)
+    ll, f32 = ctypes.c_longlong, ctypes.c_float
+    # fold_unfold: kernel smaller than the stride / patches that do not reach the map's last rows
+    rc = L.fgt_fold_unfold(one, 1, 4, 4, 40, 2, 2, 3, 0, 12, 12, 1, one, ll(0), None)
+    assert rc == -1 and "cover the stride" in L.fgt_last_error().decode()
+    rc = L.fgt_fold_unfold(one, 1, 4, 4, 40, 7, 7, 3, 3, 60, 108, 1, one, ll(0), None)
+    assert rc == -1 and "do not cover" in L.fgt_last_error().decode()
+    rc = L.fgt_fold_unfold(None, 1, 20, 36, 40, 7, 7, 3, 3, 60, 108, 1, one, ll(0), None)
+    assert rc == -1 and "fold_unfold" in L.fgt_last_error().decode()
+    # dwconv / im2col argument checks
+    rc = L.fgt_dwconv3x3_res(one, 1, 4, 4, 6, one, one, one, None, ll(0), None)
+    assert rc == -1 and "multiple of 4" in L.fgt_last_error().decode()
+    rc = L.fgt_im2col_nchw(one, 4, None, 0, 1, 8, 8, 3, 1, 1, 0, 8, 8, 32, f32(1), f32(0), one, ll(0), None)
+    assert rc == -1 and "im2col_nchw" in L.fgt_last_error().decode()       # 3*3*4 = 36 > cpad 32
+    rc = L.fgt_im2col_nchw(one, 4, None, 0, 1, 8, 4096, 7, 1, 3, 0, 8, 4096, 200, f32(1), f32(0), one, ll(0), None)
+    assert rc == -1 and "staged input rows" in L.fgt_last_error().decode()  # 7 * 4 * 4102 floats > 160 KB
+    # the fused SWMHSA operand preparation, the decoder tail and the device-side mask glue
+    rc = L.fgt_swin_prep(one, one, 512, 256, 1, 20, 36, None, 960, 1024, 4, 6, 10, one, one, one, one, one, ll(0), one, ll(0),
+                         f32(1e-5), None)
+    assert rc == -1 and "swin_prep: null" in L.fgt_last_error().decode()
+    rc = L.fgt_swin_prep(one, one, 512, 256, 1, 20, 36, one, 960, 1000, 4, 6, 10, one, one, one, one, one, ll(0), one, ll(0),
+                         f32(1e-5), None)
+    assert rc == -1 and "swin_prep" in L.fgt_last_error().decode()          # R = 1000 < 960 local + 60 pooled rows
+    rc = L.fgt_conv_tail(one, ll(0), 1, 8, 8, 64, one, ll(0), 64, 4, one, 0, one, ll(0), ll(0), ll(0), ll(0), None)
+    assert rc == -1 and "cout=4" in L.fgt_last_error().decode()
+    rc = L.fgt_conv_tail(one, ll(0), 1, 8, 8, 48, one, ll(0), 48, 3, one, 0, one, ll(0), ll(0), ll(0), ll(0), None)
+    assert rc == -1 and "conv_tail" in L.fgt_last_error().decode()          # cin must be a multiple of 64
+    rc = L.fgt_binary_dilate(one, 1, 4, 4, 1, one, one, None)
+    assert rc == -1 and "alias" in L.fgt_last_error().decode()
+    rc = L.fgt_binary_dilate(one, 1, 4, 4, 0, ctypes.c_void_p(16), ctypes.c_void_p(24), None)
+    assert rc == -1 and "binary_dilate" in L.fgt_last_error().decode()      # iterations >= 1
+    rc = L.fgt_resize_nearest_u8(one, 1, 4, 4, 1, 0, 4, one, None)
+    assert rc == -1 and "resize_nearest" in L.fgt_last_error().decode()
+    rc = L.fgt_resize_bilinear_f32(None, 1, 4, 4, 1, 8, 8, 0, f32(1), f32(1), one, None)
+    assert rc == -1 and "resize_bilinear" in L.fgt_last_error().decode()
+    rc = L.fgt_fill_holes_pass(one, 1, 4, 4, one, None, 1, None)
+    assert rc == -1 and "fill_holes" in L.fgt_last_error().decode()
